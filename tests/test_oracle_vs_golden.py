@@ -1,0 +1,113 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from /root/reference).  fp32 on both sides; tolerances cover
+summation-order differences only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clipself_oracle as O
+
+CASES = {
+    "tiny_ragged": (O.CFG_TINY, 3, 5, "proposal", True),
+    "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
+    "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False),
+}
+
+
+def _run(golden, tag, need_grad):
+    cfg, B, K, kind, ragged = CASES[tag]
+    g = golden(tag)
+    seed = int(g["seed"])
+    images, boxes, crops = O.synth_batch(cfg, B, K, seed + 2, kind=kind, ragged=ragged)
+    assert np.array_equal(boxes.numpy(), g["boxes"])                    # bit-exact boxes
+    if "images" in g.files:
+        assert np.array_equal(images.numpy(), g["images"])
+        assert np.array_equal(crops.numpy(), g["crops"])
+    else:
+        assert images.double().sum().item() == float(g["images_checksum"])
+        assert crops.double().sum().item() == float(g["crops_checksum"])
+    ssd = O.synth_tower_weights(cfg, seed)
+    tsd = O.synth_tower_weights(cfg, seed + 1)
+    if need_grad:
+        for k, v in ssd.items():
+            if k.startswith("blocks."):
+                v.requires_grad_(True)
+    out = O.clipself_step(ssd, tsd, images, boxes, crops, cfg)
+    return g, out, ssd
+
+
+@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_grid"])
+def test_forward_tiny(golden, tag):
+    g, out, _ = _run(golden, tag, need_grad=False)
+    np.testing.assert_allclose(out["teacher"].numpy(), g["teacher"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out["dense"].numpy(), g["dense_nhwc"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(out["student_roi"].numpy(), g["student_roi"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(out["loss"].item(), float(g["loss"]), rtol=1e-5)
+
+
+def test_backward_tiny(golden):
+    g, out, ssd = _run(golden, "tiny_ragged", need_grad=True)
+    out["loss"].backward()
+    names = [str(n) for n in g["grad_names"]]
+    for name, norm in zip(names, g["grad_norms"]):
+        t = ssd[name]
+        if not name.startswith("blocks."):
+            continue
+        if norm < 0:                                   # reference: grad is None
+            assert t.grad is None or float(t.grad.abs().sum()) == 0.0, name
+            continue
+        ref = g["grad/" + name]
+        np.testing.assert_allclose(t.grad.numpy(), ref, rtol=2e-3, atol=1e-7 + 2e-4 * np.abs(ref).max(),
+                                   err_msg=name)
+
+
+def test_gradless_params(golden):
+    """Last block q/k projections never receive gradient (SURVEY §7 'hard parts', a15)."""
+    g = golden("tiny_ragged")
+    last = O.CFG_TINY.layers - 1
+    none = {str(n) for n, v in zip(g["grad_names"], g["grad_norms"]) if v < 0 and str(n).startswith("blocks.")}
+    assert none == {f"blocks.{last}.attn.q_proj.weight", f"blocks.{last}.attn.k_proj.weight",
+                    f"blocks.{last}.attn.q_bias"}
+
+
+def test_mask_pool(golden):
+    g, out, _ = _run(golden, "tiny_ragged", need_grad=False)
+    B = out["dense"].shape[0]
+    boxes = torch.from_numpy(g["boxes"])
+    counts = [int((boxes[b, :, 4] > 0.5).sum()) for b in range(B)]
+    masks = torch.split(torch.from_numpy(g["masks"]), counts)
+    pooled = torch.nn.functional.normalize(O.mask_pool(out["dense"], masks), dim=-1)
+    np.testing.assert_allclose(pooled.numpy(), g["mask_pooled"], rtol=1e-4, atol=2e-6)
+
+
+def test_forward_cfg1_b16(golden):
+    """BASELINE.json configs[0] (ViT-B/16, 2x224^2, 8 patch boxes / image, fp32 CPU)."""
+    g, out, _ = _run(golden, "cfg1_b16", need_grad=False)
+    np.testing.assert_allclose(out["teacher"].numpy(), g["teacher"], rtol=2e-4, atol=5e-5)
+    np.testing.assert_allclose(out["dense"].numpy(), g["dense_nhwc"], rtol=2e-4, atol=5e-6)
+    np.testing.assert_allclose(out["student_roi"].numpy(), g["student_roi"], rtol=2e-4, atol=5e-6)
+    np.testing.assert_allclose(out["loss"].item(), float(g["loss"]), rtol=1e-5)
+
+
+def test_extract_rois_bit_exact():
+    _, boxes, _ = O.synth_batch(O.CFG_TINY, 4, 6, 7, kind="proposal", ragged=True)
+    rois, idx = O.extract_rois(boxes)
+    ref_idx = []
+    for b in range(4):
+        valid = boxes[b, :, -1] > 0.5
+        assert torch.equal(rois[b], boxes[b][valid][:, :4])
+        ref_idx += [b * 6 + int(k) for k in torch.nonzero(valid).flatten()]
+    assert idx.tolist() == ref_idx
+
+
+def test_roi_align_matches_torchvision():
+    """The restated RoIAlign against the dependency the reference calls (eva_vit_model.py:628)."""
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(0)
+    f = torch.randn(2, 7, 9, 16)
+    boxes = [torch.tensor([[0.0, 0.0, 9.0, 7.0], [1.3, 2.2, 1.9, 2.5], [4.0, 3.0, 8.999, 6.5],
+                           [8.5, 6.5, 9.0, 7.0]]),
+             torch.tensor([[2.0, 1.0, 2.0, 1.0], [0.2, 0.1, 6.7, 5.3]])]
+    ours = O.roi_align_1x1_nhwc(f, boxes)
+    ref = tv.ops.roi_align(f.permute(0, 3, 1, 2).contiguous(), boxes, (1, 1), 1.0, -1, True)[..., 0, 0]
+    np.testing.assert_allclose(ours.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
