@@ -1,0 +1,88 @@
+"""ctypes binding of libclipself_b200.so (the C ABI declared in include/clipself_b200.h).
+
+The product path has no CPU implementation: if the library is missing or a call fails this module
+raises — it never falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libclipself_b200.so")
+
+CS_F32, CS_BF16 = 0, 1
+EPI_STORE, EPI_QKV_ROPE, EPI_SWIGLU, EPI_TOKENS = 0, 1, 2, 3
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class GemmEpilogue(C.Structure):
+    """cs_gemm_epilogue_t"""
+    _fields_ = [("mode", C.c_int32), ("out_dtype", C.c_int32), ("out", vp), ("ldo", i64),
+                ("bias", vp), ("residual", vp), ("ldr", i64), ("rope_cos", vp), ("rope_sin", vp),
+                ("tokens", C.c_int32), ("rope_cols", C.c_int32), ("pos_embed", vp),
+                ("alpha", f32), ("reserved", C.c_int32)]
+
+
+# name -> argtypes, exactly the prototypes of include/clipself_b200.h
+PROTOTYPES = {
+    "cs_abi_version": [],
+    "cs_device_info": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)],
+    "cs_extract_rois": [vp, i32, i32, vp, vp, vp, vp, vp],
+    "cs_gather_rows": [vp, vp, i32, i64, vp, vp],
+    "cs_roi_align_fwd": [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp],
+    "cs_roi_align_bwd": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp],
+    "cs_mask_pool_fwd": [vp, i32, i32, i32, vp, vp, i32, vp, vp],
+    "cs_cosine_loss_fwd": [vp, vp, i32, i32, f32, vp, vp, vp],
+    "cs_cosine_loss_bwd": [vp, vp, vp, i32, i32, f32, vp, vp, vp],
+    "cs_l2norm_fwd": [vp, i64, i32, vp, vp, vp],
+    "cs_l2norm_bwd": [vp, vp, vp, i64, i32, vp, vp],
+    "cs_im2col_patches": [vp, i32, i32, i32, i32, vp, i64, vp],
+    "cs_fill_cls_rows": [vp, vp, i32, i32, i32, vp, vp],
+    "cs_layernorm_fwd": [vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, f32, vp, i64, vp, vp, vp],
+    "cs_gemm_bf16": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],
+    "cs_pack_swiglu_weights": [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp],
+    "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp],
+    "cs_cast_pad_bf16": [vp, i64, i64, i64, vp, i64, vp],
+}
+
+_lib = None
+
+
+class ClipselfB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ClipselfB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m clipself_b200.build` "
+                "(there is no CPU / PyTorch fallback for this path)")
+        l = C.CDLL(LIB_PATH)
+        l.cs_last_error.restype = C.c_char_p
+        l.cs_last_error.argtypes = []
+        for name, args in PROTOTYPES.items():
+            fn = getattr(l, name)          # AttributeError if the .so does not export it
+            fn.restype = C.c_int
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise ClipselfB200Error(f"{what} failed (code {rc}): {lib().cs_last_error().decode()}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)
+
+
+def require_device() -> dict:
+    """Raise unless the current CUDA device is an sm_100 part."""
+    sm, n, mem = i32(), i32(), i64()
+    call("cs_device_info", C.byref(sm), C.byref(n), C.byref(mem))
+    return dict(sm=sm.value, num_sms=n.value, hbm_bytes=mem.value)

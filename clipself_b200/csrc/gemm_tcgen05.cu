@@ -1,0 +1,508 @@
+// tcgen05 / TMA / TMEM GEMM for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T  (bf16 in, f32 accumulate)
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 64-wide K slabs)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Pipelines: smem ring full/empty (TMA <-> MMA), double-buffered TMEM accumulator full/empty
+// (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Fused epilogues (cs_epilogue_mode_t): bias / residual / alpha, RoPE on the q|k columns
+// (rope.py:148-164 semantics), SwiGLU gate*up on packed weights, patch-embed token assembly.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cs {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two)
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
+};
+
+struct EpiParams {
+    int mode;
+    int out_bf16;
+    void* out;
+    long long ldo;
+    const float* bias;
+    const float* residual;
+    long long ldr;
+    const float* rope_cos;
+    const float* rope_sin;
+    int tokens;
+    int rope_cols;
+    const float* pos_embed;
+    float alpha;
+};
+
+// ----------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
+                                            int c_inner, int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+        "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on the mbarrier once every previously issued tcgen05.mma of this thread completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B
+//   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7,10), K-major both,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------
+// Epilogue math on one 32-column chunk held by one thread (one output row)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j], v[j + 1]);
+        u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]);
+        u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = u;
+    }
+}
+__device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restrict__ src) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(src + j);
+        v[j] += b.x;
+        v[j + 1] += b.y;
+        v[j + 2] += b.z;
+        v[j + 3] += b.w;
+    }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            int M, int N, int K, const EpiParams ep) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
+    uint8_t* smem = smem_raw + (base - raw_addr);
+
+    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m_tiles * num_n_tiles;
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4 * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n_tiles) * BLOCK_M;
+                const int n0 = (tile % num_n_tiles) * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = base + stage * C::STAGE_BYTES;
+                    const uint32_t sb = sa + C::A_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m0);
+                    tma_load_2d(sb, &map_b, full_bar(stage), kb * BLOCK_K, n0);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer --------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);         // TMA bytes landed
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * C::STAGE_BYTES;
+                    const uint32_t sb = sa + C::A_BYTES;
+                    const uint64_t da = make_smem_desc(sa);
+                    const uint64_t db = make_smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr>>4)
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));             // frees the smem slot when MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------ epilogue -----------------------------------
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / num_n_tiles) * BLOCK_M;
+            const int n0 = (tile % num_n_tiles) * BLOCK_N;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            const int m = m0 + row_in_tile;
+            const bool row_ok = m < M;
+
+            if (ep.mode == CS_EPI_SWIGLU) {
+                // packed tile: columns [0,128) gate, [128,256) up of hidden columns n0/2 + [0,128)
+                if constexpr (BLOCK_N == 256) {
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t rg[32], ru[32];
+                        tmem_ld32(taddr + c * 32, rg);
+                        tmem_ld32(taddr + 128 + c * 32, ru);
+                        tmem_ld_wait();
+                        float h[32];
+                        const float* bg = ep.bias + n0 + c * 32;
+                        const float* bu = ep.bias + n0 + 128 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float g = __uint_as_float(rg[j]) * ep.alpha + __ldg(bg + j);
+                            const float u = __uint_as_float(ru[j]) * ep.alpha + __ldg(bu + j);
+                            h[j] = (g / (1.0f + __expf(-g))) * u;
+                        }
+                        if (row_ok) {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.out) +
+                                                 (long long)m * ep.ldo + (n0 >> 1) + c * 32;
+                            store_row_bf16(dst, h);
+                        }
+                    }
+                }
+            } else {
+                long long out_row = m;
+                int pos_row = 0;
+                if (ep.mode == CS_EPI_TOKENS) {
+                    const int per = ep.tokens - 1;
+                    out_row = (long long)m + m / per + 1;
+                    pos_row = m % per + 1;
+                }
+                const int tok = (ep.mode == CS_EPI_QKV_ROPE) ? (m % ep.tokens) : 0;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    const int n = n0 + c * 32;
+                    if (n >= N) break;                      // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+                    if (ep.bias != nullptr) add_vec32(v, ep.bias + n);
+                    if (ep.mode == CS_EPI_QKV_ROPE) {
+                        if (n < ep.rope_cols && tok > 0 && row_ok) {
+                            const int d0 = n & 63;
+                            const float* cs_ = ep.rope_cos + (long long)(tok - 1) * 64 + d0;
+                            const float* sn_ = ep.rope_sin + (long long)(tok - 1) * 64 + d0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float x0 = v[j], x1 = v[j + 1];
+                                v[j] = x0 * __ldg(cs_ + j) - x1 * __ldg(sn_ + j);
+                                v[j + 1] = x1 * __ldg(cs_ + j + 1) + x0 * __ldg(sn_ + j + 1);
+                            }
+                        }
+                    } else if (ep.mode == CS_EPI_TOKENS) {
+                        if (row_ok) add_vec32(v, ep.pos_embed + (long long)pos_row * N + n);
+                    }
+                    if (row_ok) {
+                        if (ep.residual != nullptr) add_vec32(v, ep.residual + out_row * ep.ldr + n);
+                        if (ep.out_bf16)
+                            store_row_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + n, v);
+                        else
+                            store_row_f32(reinterpret_cast<float*>(ep.out) + out_row * ep.ldo + n, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with leading dimension ld; box = [box_rows, 64 cols], 128B swizzle.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return CS_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld", (int)r, ptr,
+                  (long long)rows, (long long)cols, (long long)ld);
+        return CS_ERR_CUDA;
+    }
+    return CS_OK;
+}
+
+template <int BLOCK_N>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
+                  cudaStream_t stream) {
+    using C = Cfg<BLOCK_N>;
+    static bool configured = false;
+    if (!configured) {
+        CS_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+}  // namespace gemm
+}  // namespace cs
+
+extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int N,
+                            int K, const cs_gemm_epilogue_t* e, void* stream) {
+    using namespace cs;
+    using namespace cs::gemm;
+    CS_CHECK_ARG(A && W && e && e->out, "cs_gemm_bf16: null pointer");
+    CS_CHECK_ARG(M > 0 && N > 0 && K > 0 && M < (1ll << 31), "cs_gemm_bf16: bad shape M=%lld N=%d K=%d",
+                 (long long)M, N, K);
+    CS_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K,
+                 "cs_gemm_bf16: lda/ldw must be multiples of 8 and >= K (lda=%lld ldw=%lld K=%d)",
+                 (long long)lda, (long long)ldw, K);
+    CS_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "cs_gemm_bf16: A/W must be 16 B aligned");
+    CS_CHECK_ARG(N % 32 == 0, "cs_gemm_bf16: N must be a multiple of 32 (N=%d)", N);
+    CS_CHECK_ARG(e->mode >= CS_EPI_STORE && e->mode <= CS_EPI_TOKENS, "cs_gemm_bf16: bad epilogue mode %d", e->mode);
+    CS_CHECK_ARG(((uintptr_t)e->out % 16 == 0) && (e->ldo % (e->out_dtype == CS_BF16 ? 8 : 4) == 0),
+                 "cs_gemm_bf16: out must be 16 B aligned with 16 B aligned rows");
+    if (e->residual) CS_CHECK_ARG(((uintptr_t)e->residual % 16 == 0) && e->ldr % 4 == 0, "cs_gemm_bf16: residual alignment");
+    if (e->bias) CS_CHECK_ARG((uintptr_t)e->bias % 16 == 0, "cs_gemm_bf16: bias alignment");
+
+    EpiParams ep;
+    ep.mode = e->mode;
+    ep.out_bf16 = e->out_dtype == CS_BF16;
+    ep.out = e->out;
+    ep.ldo = e->ldo;
+    ep.bias = e->bias;
+    ep.residual = e->residual;
+    ep.ldr = e->ldr;
+    ep.rope_cos = e->rope_cos;
+    ep.rope_sin = e->rope_sin;
+    ep.tokens = e->tokens;
+    ep.rope_cols = e->rope_cols;
+    ep.pos_embed = e->pos_embed;
+    ep.alpha = e->alpha;
+
+    bool use256 = (N % 256 == 0);
+    if (e->mode == CS_EPI_SWIGLU) {
+        CS_CHECK_ARG(N % 256 == 0 && e->bias && e->out_dtype == CS_BF16,
+                     "cs_gemm_bf16: SWIGLU needs packed N %% 256 == 0, bias, bf16 out");
+        use256 = true;
+    }
+    if (e->mode == CS_EPI_QKV_ROPE)
+        CS_CHECK_ARG(e->rope_cos && e->rope_sin && e->tokens > 1 && e->rope_cols % 64 == 0 && e->out_dtype == CS_BF16,
+                     "cs_gemm_bf16: QKV_ROPE needs tables, tokens, rope_cols %% 64 == 0, bf16 out");
+    if (e->mode == CS_EPI_TOKENS)
+        CS_CHECK_ARG(e->pos_embed && e->tokens > 1 && e->out_dtype == CS_F32 && ((uintptr_t)e->pos_embed % 16 == 0),
+                     "cs_gemm_bf16: TOKENS needs pos_embed, tokens, f32 out");
+
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, A, M, K, lda, BLOCK_M);
+    if (rc) return rc;
+    rc = make_map(&mb, W, N, K, ldw, use256 ? 256 : 128);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return use256 ? launch<256>(ma, mb, (int)M, N, K, ep, st) : launch<128>(ma, mb, (int)M, N, K, ep, st);
+}

@@ -1,0 +1,478 @@
+// Region path of the CLIPSelf step: index extraction, RoIAlign (1x1, adaptive, aligned) forward /
+// backward on NHWC maps, mask pooling, L2-normalise + cosine loss.  HBM-bound CUDA-core kernels:
+// every global access is coalesced over the channel axis; each feature map is read from HBM once
+// (staged in shared memory per image x channel-slice) and box results are written once.
+#include "common.cuh"
+
+namespace cs {
+namespace region {
+
+// ------------------------------------------------------------------------------------------
+// Index extraction (clipself.py:29-36): stable, image-major compaction of rows with box[4] > 0.5
+// ------------------------------------------------------------------------------------------
+__global__ void extract_rois_kernel(const float* __restrict__ boxes, int B, int K, float* __restrict__ rois,
+                                    int* __restrict__ crop_index, int* __restrict__ roi_batch,
+                                    int* __restrict__ img_offsets) {
+    extern __shared__ int s_off[];   // B + 1
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int n = 0;
+        for (int k = 0; k < K; ++k) n += boxes[((long long)b * K + k) * 5 + 4] > 0.5f;
+        s_off[b + 1] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_off[0] = 0;
+        for (int b = 0; b < B; ++b) s_off[b + 1] += s_off[b];
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= B; b += blockDim.x) img_offsets[b] = s_off[b];
+    for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+        const int b = i / K, k = i % K;
+        const float* row = boxes + (long long)i * 5;
+        if (!(row[4] > 0.5f)) continue;
+        int before = 0;
+        for (int j = 0; j < k; ++j) before += boxes[((long long)b * K + j) * 5 + 4] > 0.5f;
+        const int dst = s_off[b] + before;
+        rois[dst * 4 + 0] = row[0];
+        rois[dst * 4 + 1] = row[1];
+        rois[dst * 4 + 2] = row[2];
+        rois[dst * 4 + 3] = row[3];
+        crop_index[dst] = i;
+        roi_batch[dst] = b;
+    }
+}
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ index,
+                                   long long row_vecs, uint4* __restrict__ dst) {
+    const long long r = blockIdx.y;
+    const uint4* s = src + (long long)index[r] * row_vecs;
+    uint4* d = dst + r * row_vecs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row_vecs;
+         i += (long long)gridDim.x * blockDim.x)
+        d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// RoIAlign separable weights.  For output 1x1 / aligned=True the sample grid is a tensor product
+// so the pooled value is  sum_y sum_x Wy[y] Wx[x] f[y,x]  with Wy/Wx accumulated over the 1-D
+// sample positions (torchvision semantics restated in oracle/clipself_oracle.py).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void axis_weights(float lo_n, float hi_n, int size, float* __restrict__ w,
+                                             int* count_out) {
+    // denormalise exactly like eva_vit_model.py:660-662 (f32 multiply), then torchvision's
+    // aligned=True offset.
+    // (explicit _rn intrinsics: no FMA contraction, so the sample positions round exactly like
+    //  the separate multiply / subtract kernels of the reference)
+    const float lo = __fmul_rn(lo_n, (float)size);
+    const float hi = __fmul_rn(hi_n, (float)size);
+    const float start = __fsub_rn(lo, 0.5f);
+    const float end = __fsub_rn(hi, 0.5f);
+    const float roi = __fsub_rn(end, start);
+    const int grid = (int)ceilf(roi);
+    for (int i = 0; i < size; ++i) w[i] = 0.f;
+    for (int i = 0; i < grid; ++i) {
+        float p = __fadd_rn(start, __fdiv_rn(__fmul_rn((float)i + 0.5f, roi), (float)grid));
+        if (p < -1.0f || p > (float)size) continue;
+        if (p <= 0.f) p = 0.f;
+        int lo_i = (int)p, hi_i;
+        if (lo_i >= size - 1) {
+            hi_i = lo_i = size - 1;
+            p = (float)lo_i;
+        } else {
+            hi_i = lo_i + 1;
+        }
+        const float l = __fsub_rn(p, (float)lo_i);
+        const float h = __fsub_rn(1.0f, l);
+        w[lo_i] += h;
+        w[hi_i] += l;
+    }
+    *count_out = grid;
+}
+
+__global__ void roi_weights_kernel(const float* __restrict__ rois, int R, int H, int W, float* __restrict__ wy,
+                                   float* __restrict__ wx) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* b = rois + (long long)r * 4;
+    int gw, gh;
+    axis_weights(b[0], b[2], W, wx + (long long)r * W, &gw);
+    axis_weights(b[1], b[3], H, wy + (long long)r * H, &gh);
+    const float count = (float)max(gw * gh, 1);
+    const float inv = 1.0f / count;
+    for (int i = 0; i < H; ++i) wy[(long long)r * H + i] *= inv;
+}
+
+constexpr int ROI_CS = 64;       // channel slice per CTA
+constexpr int ROI_LANES = 4;     // roi (or pixel) lanes per CTA
+constexpr int ROI_THREADS = ROI_CS * ROI_LANES;
+
+// out[r, c] = sum_{y,x} wy[r,y] wx[r,x] f[b,y,x,c];  grid (C/64, B)
+template <bool kStage>
+__global__ void __launch_bounds__(ROI_THREADS)
+roi_align_fwd_kernel(const float* __restrict__ fmap, int H, int W, int C, const int* __restrict__ img_offsets,
+                     const float* __restrict__ wy, const float* __restrict__ wx, float* __restrict__ out) {
+    extern __shared__ float s_map[];   // [H*W][ROI_CS] when staged
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * ROI_CS;
+    const int c = threadIdx.x % ROI_CS;
+    const int lane = threadIdx.x / ROI_CS;
+    const int begin = img_offsets[b], end = img_offsets[b + 1];
+    if (begin == end) return;
+    const float* g = fmap + (long long)b * H * W * C + c0;
+    const bool c_ok = c0 + c < C;
+    if (kStage) {
+        for (int i = threadIdx.x; i < H * W * ROI_CS; i += ROI_THREADS) {
+            const int p = i / ROI_CS, cc = i % ROI_CS;
+            s_map[i] = (c0 + cc < C) ? g[(long long)p * C + cc] : 0.f;
+        }
+        __syncthreads();
+    }
+    for (int r = begin + lane; r < end; r += ROI_LANES) {
+        const float* wyr = wy + (long long)r * H;
+        const float* wxr = wx + (long long)r * W;
+        float acc = 0.f;
+        for (int y = 0; y < H; ++y) {
+            const float a = wyr[y];
+            if (a == 0.f) continue;
+            float row = 0.f;
+            for (int x = 0; x < W; ++x) {
+                const float bx = wxr[x];
+                if (bx == 0.f) continue;
+                const float f = kStage ? s_map[(y * W + x) * ROI_CS + c]
+                                       : (c_ok ? g[(long long)(y * W + x) * C + c] : 0.f);
+                row = fmaf(bx, f, row);
+            }
+            acc = fmaf(a, row, acc);
+        }
+        if (c_ok) out[(long long)r * C + c0 + c] = acc;
+    }
+}
+
+// d_fmap[b,y,x,c] = sum_{r in image b} wy[r,y] wx[r,x] d_out[r,c];  grid (C/64, B).  Gather form:
+// deterministic, every d_fmap element written exactly once.
+__global__ void __launch_bounds__(ROI_THREADS)
+roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const int* __restrict__ img_offsets,
+                     const float* __restrict__ wy, const float* __restrict__ wx, float* __restrict__ d_fmap) {
+    extern __shared__ float s_buf[];   // per roi chunk: d_out [32][ROI_CS], wy [32][H], wx [32][W]
+    constexpr int CH = 32;
+    float* s_do = s_buf;
+    float* s_wy = s_do + CH * ROI_CS;
+    float* s_wx = s_wy + CH * H;
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * ROI_CS;
+    const int c = threadIdx.x % ROI_CS;
+    const int lane = threadIdx.x / ROI_CS;
+    const int begin = img_offsets[b], end = img_offsets[b + 1];
+    const bool c_ok = c0 + c < C;
+    float* g = d_fmap + (long long)b * H * W * C + c0;
+    const int HW = H * W;
+    if (begin == end) {                      // image without boxes: its gradient slice is zero
+        for (int p = lane; p < HW; p += ROI_LANES)
+            if (c_ok) g[(long long)p * C + c] = 0.f;
+        return;
+    }
+    // rois are processed in chunks of CH staged in shared memory; images with more than CH rois
+    // accumulate the later chunks onto the slice written by the first one (same thread, no race).
+    for (int r0 = begin; r0 < end; r0 += CH) {
+        const int n = min(CH, end - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * ROI_CS; i += ROI_THREADS) {
+            const int rr = i / ROI_CS, cc = i % ROI_CS;
+            s_do[i] = (c0 + cc < C) ? d_out[(long long)(r0 + rr) * C + c0 + cc] : 0.f;
+        }
+        for (int i = threadIdx.x; i < n * H; i += ROI_THREADS) s_wy[i] = wy[(long long)r0 * H + i];
+        for (int i = threadIdx.x; i < n * W; i += ROI_THREADS) s_wx[i] = wx[(long long)r0 * W + i];
+        __syncthreads();
+        for (int p = lane; p < HW; p += ROI_LANES) {
+            const int y = p / W, x = p % W;
+            float acc = 0.f;
+            for (int rr = 0; rr < n; ++rr) {
+                const float wgt = s_wy[rr * H + y] * s_wx[rr * W + x];
+                acc = fmaf(wgt, s_do[rr * ROI_CS + c], acc);
+            }
+            if (c_ok) {
+                float* dst = g + (long long)p * C + c;
+                *dst = (r0 == begin) ? acc : (*dst + acc);
+            }
+        }
+    }
+}
+
+// out[r,c] = sum_p m[r,p] f[b,p,c] / (sum_p m[r,p] + 1e-12);  grid (C/64, B)
+template <bool kStage>
+__global__ void __launch_bounds__(ROI_THREADS)
+mask_pool_kernel(const float* __restrict__ fmap, int HW, int C, const float* __restrict__ masks,
+                 const int* __restrict__ img_offsets, float* __restrict__ out) {
+    extern __shared__ float s_map[];
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * ROI_CS;
+    const int c = threadIdx.x % ROI_CS;
+    const int lane = threadIdx.x / ROI_CS;
+    const int begin = img_offsets[b], end = img_offsets[b + 1];
+    if (begin == end) return;
+    const float* g = fmap + (long long)b * HW * C + c0;
+    const bool c_ok = c0 + c < C;
+    if (kStage) {
+        for (int i = threadIdx.x; i < HW * ROI_CS; i += ROI_THREADS) {
+            const int p = i / ROI_CS, cc = i % ROI_CS;
+            s_map[i] = (c0 + cc < C) ? g[(long long)p * C + cc] : 0.f;
+        }
+        __syncthreads();
+    }
+    for (int r = begin + lane; r < end; r += ROI_LANES) {
+        const float* m = masks + (long long)r * HW;
+        float acc = 0.f, msum = 0.f;
+        for (int p = 0; p < HW; ++p) {
+            const float w = m[p];
+            msum += w;
+            if (w == 0.f) continue;
+            const float f = kStage ? s_map[p * ROI_CS + c] : (c_ok ? g[(long long)p * C + c] : 0.f);
+            acc = fmaf(w, f, acc);
+        }
+        if (c_ok) out[(long long)r * C + c0 + c] = acc / (msum + 1e-12f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// cosine loss (clipself.py:42-47) and row L2 normalisation (eva_vit_model.py:620)
+// ------------------------------------------------------------------------------------------
+__global__ void cosine_rows_kernel(const float* __restrict__ s, const float* __restrict__ t, int R, int C,
+                                   float* __restrict__ stats) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float4* sp = reinterpret_cast<const float4*>(s + (long long)r * C);
+    const float4* tp = reinterpret_cast<const float4*>(t + (long long)r * C);
+    float ss = 0.f, tt = 0.f, st = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 a = sp[i], b = tp[i];
+        ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        tt += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+        st += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }
+    ss = warp_sum(ss);
+    tt = warp_sum(tt);
+    st = warp_sum(st);
+    if (lane == 0) {
+        const float is = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        const float it = 1.0f / fmaxf(sqrtf(tt), 1e-12f);
+        stats[r * 3 + 0] = is;
+        stats[r * 3 + 1] = it;
+        stats[r * 3 + 2] = st * is * it;
+    }
+}
+
+// single CTA, fixed-order tree: loss = (1 - sum(cos)/R) * weight
+__global__ void cosine_reduce_kernel(const float* __restrict__ stats, int R, float weight, float* __restrict__ loss) {
+    __shared__ float s_part[1024];
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) acc += stats[r * 3 + 2];
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (1.0f - s_part[0] / (float)R) * weight;
+}
+
+__global__ void cosine_bwd_kernel(const float* __restrict__ s, const float* __restrict__ t,
+                                  const float* __restrict__ stats, int R, int C, float weight,
+                                  const float* __restrict__ d_loss, float* __restrict__ d_s) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float is = stats[r * 3 + 0], it = stats[r * 3 + 1], cs_ = stats[r * 3 + 2];
+    const float k = -d_loss[0] * weight / (float)R;
+    const float4* sp = reinterpret_cast<const float4*>(s + (long long)r * C);
+    const float4* tp = reinterpret_cast<const float4*>(t + (long long)r * C);
+    float4* dp = reinterpret_cast<float4*>(d_s + (long long)r * C);
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 a = sp[i], b = tp[i];
+        float4 d;
+        d.x = k * is * (b.x * it - cs_ * a.x * is);
+        d.y = k * is * (b.y * it - cs_ * a.y * is);
+        d.z = k * is * (b.z * it - cs_ * a.z * is);
+        d.w = k * is * (b.w * it - cs_ * a.w * is);
+        dp[i] = d;
+    }
+}
+
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, long long M, int C, float* __restrict__ y,
+                                  float* __restrict__ inv_norm) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= M) return;
+    const float4* xp = reinterpret_cast<const float4*>(x + r * C);
+    float4* yp = reinterpret_cast<float4*>(y + r * C);
+    float ss = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 a = xp[i];
+        ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int i = lane; i < C / 4; i += 32) {
+        float4 a = xp[i];
+        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+        yp[i] = a;
+    }
+    if (lane == 0 && inv_norm) inv_norm[r] = inv;
+}
+
+// dx = inv * (dy - y * <y, dy>)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ inv_norm,
+                                  const float* __restrict__ dy, long long M, int C, float* __restrict__ dx) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= M) return;
+    const float4* yp = reinterpret_cast<const float4*>(y + r * C);
+    const float4* gp = reinterpret_cast<const float4*>(dy + r * C);
+    float4* dp = reinterpret_cast<float4*>(dx + r * C);
+    float dot = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 a = yp[i], g = gp[i];
+        dot += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+    }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[r];
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 a = yp[i], g = gp[i];
+        float4 d;
+        d.x = inv * (g.x - a.x * dot);
+        d.y = inv * (g.y - a.y * dot);
+        d.z = inv * (g.z - a.z * dot);
+        d.w = inv * (g.w - a.w * dot);
+        dp[i] = d;
+    }
+}
+
+}  // namespace region
+}  // namespace cs
+
+using namespace cs;
+using namespace cs::region;
+
+extern "C" int cs_extract_rois(const float* normed_boxes, int B, int K, float* rois, int32_t* crop_index,
+                               int32_t* roi_batch, int32_t* img_offsets, void* stream) {
+    CS_CHECK_ARG(normed_boxes && rois && crop_index && roi_batch && img_offsets, "cs_extract_rois: null pointer");
+    CS_CHECK_ARG(B > 0 && K > 0 && B <= 8192, "cs_extract_rois: bad shape B=%d K=%d", B, K);
+    extract_rois_kernel<<<1, 1024, (B + 1) * sizeof(int), (cudaStream_t)stream>>>(normed_boxes, B, K, rois,
+                                                                                  crop_index, roi_batch,
+                                                                                  img_offsets);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_gather_rows(const void* src, const int32_t* index, int R, int64_t row_bytes, void* dst,
+                              void* stream) {
+    CS_CHECK_ARG(src && index && dst, "cs_gather_rows: null pointer");
+    CS_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "cs_gather_rows: row_bytes must be a multiple of 16");
+    if (R == 0) return CS_OK;
+    const long long vecs = row_bytes / 16;
+    dim3 grid((unsigned)min((long long)64, (vecs + 255) / 256), R);
+    gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, index, vecs, (uint4*)dst);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+static int stage_bytes(int hw) { return hw * ROI_CS * (int)sizeof(float); }
+constexpr int kMaxStage = 200 * 1024;
+
+extern "C" int cs_roi_align_fwd(const float* fmap, int B, int H, int W, int C, const float* rois,
+                                const int32_t* img_offsets, int R, float* wy, float* wx, float* out,
+                                void* stream) {
+    CS_CHECK_ARG(fmap && rois && img_offsets && wy && wx && out, "cs_roi_align_fwd: null pointer");
+    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0, "cs_roi_align_fwd: bad shape");
+    if (R == 0) return CS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    roi_weights_kernel<<<ceil_div(R, 128), 128, 0, st>>>(rois, R, H, W, wy, wx);
+    CS_LAUNCH_CHECK();
+    dim3 grid(ceil_div(C, ROI_CS), B);
+    const int smem = stage_bytes(H * W);
+    if (smem <= kMaxStage) {
+        static bool configured = false;
+        if (!configured) {
+            CS_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+            configured = true;
+        }
+        roi_align_fwd_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fmap, H, W, C, img_offsets, wy, wx, out);
+    } else {
+        roi_align_fwd_kernel<false><<<grid, ROI_THREADS, 0, st>>>(fmap, H, W, C, img_offsets, wy, wx, out);
+    }
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_roi_align_bwd(const float* d_out, int B, int H, int W, int C, const int32_t* img_offsets,
+                                int R, const float* wy, const float* wx, float* d_fmap, void* stream) {
+    CS_CHECK_ARG(d_out && img_offsets && wy && wx && d_fmap, "cs_roi_align_bwd: null pointer");
+    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0, "cs_roi_align_bwd: bad shape");
+    dim3 grid(ceil_div(C, ROI_CS), B);
+    const int smem = (32 * ROI_CS + 32 * H + 32 * W) * (int)sizeof(float);
+    CS_CHECK_ARG(smem <= 48 * 1024, "cs_roi_align_bwd: H+W too large (%d,%d)", H, W);
+    roi_align_bwd_kernel<<<grid, ROI_THREADS, smem, (cudaStream_t)stream>>>(d_out, H, W, C, img_offsets, wy, wx,
+                                                                           d_fmap);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_mask_pool_fwd(const float* fmap, int B, int HW, int C, const float* masks,
+                                const int32_t* img_offsets, int R, float* out, void* stream) {
+    CS_CHECK_ARG(fmap && masks && img_offsets && out, "cs_mask_pool_fwd: null pointer");
+    CS_CHECK_ARG(B > 0 && HW > 0 && C > 0 && R >= 0, "cs_mask_pool_fwd: bad shape");
+    if (R == 0) return CS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ceil_div(C, ROI_CS), B);
+    const int smem = stage_bytes(HW);
+    if (smem <= kMaxStage) {
+        static bool configured = false;
+        if (!configured) {
+            CS_CUDA(cudaFuncSetAttribute(mask_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+            configured = true;
+        }
+        mask_pool_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fmap, HW, C, masks, img_offsets, out);
+    } else {
+        mask_pool_kernel<false><<<grid, ROI_THREADS, 0, st>>>(fmap, HW, C, masks, img_offsets, out);
+    }
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_cosine_loss_fwd(const float* s, const float* t, int R, int C, float weight, float* loss,
+                                  float* row_stats, void* stream) {
+    CS_CHECK_ARG(s && t && loss && row_stats, "cs_cosine_loss_fwd: null pointer");
+    CS_CHECK_ARG(R > 0 && C > 0 && C % 4 == 0, "cs_cosine_loss_fwd: bad shape R=%d C=%d", R, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    cosine_rows_kernel<<<ceil_div(R, 8), 256, 0, st>>>(s, t, R, C, row_stats);
+    CS_LAUNCH_CHECK();
+    cosine_reduce_kernel<<<1, 1024, 0, st>>>(row_stats, R, weight, loss);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_cosine_loss_bwd(const float* s, const float* t, const float* row_stats, int R, int C,
+                                  float weight, const float* d_loss, float* d_s, void* stream) {
+    CS_CHECK_ARG(s && t && row_stats && d_loss && d_s, "cs_cosine_loss_bwd: null pointer");
+    CS_CHECK_ARG(R > 0 && C > 0 && C % 4 == 0, "cs_cosine_loss_bwd: bad shape R=%d C=%d", R, C);
+    cosine_bwd_kernel<<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>(s, t, row_stats, R, C, weight, d_loss, d_s);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_l2norm_fwd(const float* x, int64_t M, int C, float* y, float* inv_norm, void* stream) {
+    CS_CHECK_ARG(x && y, "cs_l2norm_fwd: null pointer");
+    CS_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "cs_l2norm_fwd: bad shape");
+    l2norm_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, M, C, y, inv_norm);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_l2norm_bwd(const float* y, const float* inv_norm, const float* d_y, int64_t M, int C,
+                             float* d_x, void* stream) {
+    CS_CHECK_ARG(y && inv_norm && d_y && d_x, "cs_l2norm_bwd: null pointer");
+    CS_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "cs_l2norm_bwd: bad shape");
+    l2norm_bwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(y, inv_norm, d_y, M, C, d_x);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}

@@ -1,0 +1,255 @@
+// Row / element-wise kernels of the EVA02 tower: LayerNorm, patch gather (im2col), CLS rows,
+// casts and weight packing.  All HBM-bound: one pass over the data, 128-bit accesses, f32 math.
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace cs {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+namespace rowops {
+
+constexpr int LN_WARPS = 8;
+
+// One warp per row.  The row is staged in shared memory (single HBM read), statistics are the
+// two-pass mean / centred variance in f32 (same numerics as ATen's layer_norm).
+template <typename TIn>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const TIn* __restrict__ x, long long ldx, long long M, int D, int row_div, int row_mul,
+                     int row_off, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out) {
+    extern __shared__ float s_rows[];   // LN_WARPS * D
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * LN_WARPS + warp;
+    if (m >= M) return;
+    const long long prow = m * row_mul + (row_div > 0 ? m / row_div : 0) + row_off;
+    const TIn* xr = x + prow * ldx;
+    float* s = s_rows + warp * D;
+    float sum = 0.f;
+    if constexpr (sizeof(TIn) == 4) {
+        for (int i = lane * 4; i < D; i += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + i);
+            *reinterpret_cast<float4*>(s + i) = v;
+            sum += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (int i = lane * 8; i < D; i += 256) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + i);
+            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+            *reinterpret_cast<float4*>(s + i) = make_float4(a.x, a.y, b.x, b.y);
+            *reinterpret_cast<float4*>(s + i + 4) = make_float4(c.x, c.y, d.x, d.y);
+            sum += ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+        }
+    }
+    sum = warp_sum(sum);
+    const float mean = sum / (float)D;
+    __syncwarp();
+    float var = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + i);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        var += (a * a + b * b) + (c * c + d * d);
+    }
+    var = warp_sum(var);
+    const float rstd = rsqrtf(var / (float)D + eps);
+    __nv_bfloat16* yr = y + m * ldy;
+    for (int i = lane * 8; i < D; i += 256) {
+        const float4 v0 = *reinterpret_cast<const float4*>(s + i);
+        const float4 v1 = *reinterpret_cast<const float4*>(s + i + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + i);
+        const float4 g1 = *reinterpret_cast<const float4*>(gamma + i + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + i);
+        const float4 b1 = *reinterpret_cast<const float4*>(beta + i + 4);
+        uint4 o;
+        o.x = pack_bf16((v0.x - mean) * rstd * g0.x + b0.x, (v0.y - mean) * rstd * g0.y + b0.y);
+        o.y = pack_bf16((v0.z - mean) * rstd * g0.z + b0.z, (v0.w - mean) * rstd * g0.w + b0.w);
+        o.z = pack_bf16((v1.x - mean) * rstd * g1.x + b1.x, (v1.y - mean) * rstd * g1.y + b1.y);
+        o.w = pack_bf16((v1.z - mean) * rstd * g1.z + b1.z, (v1.w - mean) * rstd * g1.w + b1.w);
+        *reinterpret_cast<uint4*>(yr + i) = o;
+    }
+    if (lane == 0) {
+        if (mean_out) mean_out[m] = mean;
+        if (rstd_out) rstd_out[m] = rstd;
+    }
+}
+
+// images [B,3,S,S] -> patches [B*g*g, ldp] bf16, column = c*P*P + py*P + px  (flattened conv weight
+// order).  One CTA per (image, patch row): each image row segment is read contiguously.
+template <typename TIn>
+__global__ void im2col_kernel(const TIn* __restrict__ img, int S, int P, __nv_bfloat16* __restrict__ out,
+                              long long ldp) {
+    const int g = S / P;
+    const int b = blockIdx.y, gy = blockIdx.x;
+    const int kreal = 3 * P * P;
+    // iterate over (c, py, x) with x the full image row -> coalesced reads
+    for (int i = threadIdx.x; i < 3 * P * S; i += blockDim.x) {
+        const int x = i % S;
+        const int py = (i / S) % P;
+        const int c = i / (S * P);
+        const float v = (float)img[(((long long)b * 3 + c) * S + (gy * P + py)) * S + x];
+        const int gx = x / P, px = x % P;
+        if (gx < g) out[((long long)(b * g + gy) * g + gx) * ldp + c * P * P + py * P + px] = __float2bfloat16(v);
+    }
+    // zero the padding columns [kreal, ldp)
+    const int pad = (int)ldp - kreal;
+    for (int i = threadIdx.x; i < g * pad; i += blockDim.x) {
+        const int gx = i / pad, j = i % pad;
+        out[((long long)(b * g + gy) * g + gx) * ldp + kreal + j] = __float2bfloat16(0.f);
+    }
+}
+
+__global__ void fill_cls_kernel(const float* __restrict__ cls, const float* __restrict__ pos, int N, int D,
+                                float* __restrict__ x) {
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) x[(long long)b * N * D + i] = cls[i] + pos[i];
+}
+
+__global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, long long cols, long long lds,
+                                __nv_bfloat16* __restrict__ dst, long long ldd) {
+    const long long total = rows * ldd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ldd, c = i % ldd;
+        dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
+    }
+}
+
+// packed row (t*256 + j) = w1 row (t*128 + j); packed row (t*256 + 128 + j) = w2 row (t*128 + j)
+template <typename TIn>
+__global__ void pack_swiglu_kernel(const TIn* __restrict__ w1, const TIn* __restrict__ w2, int Hd, int K,
+                                   const float* __restrict__ b1, const float* __restrict__ b2,
+                                   __nv_bfloat16* __restrict__ packed, long long ldk, float* __restrict__ bias12) {
+    const int prow = blockIdx.x;                 // packed row
+    const int t = prow / 256, j = prow % 256;
+    const bool gate = j < 128;
+    const int src = t * 128 + (gate ? j : j - 128);
+    const TIn* w = gate ? w1 : w2;
+    const bool ok = src < Hd;
+    for (int k = threadIdx.x; k < ldk; k += blockDim.x)
+        packed[(long long)prow * ldk + k] = __float2bfloat16((ok && k < K) ? (float)w[(long long)src * K + k] : 0.f);
+    if (threadIdx.x == 0 && bias12) bias12[prow] = ok ? (gate ? b1[src] : b2[src]) : 0.f;
+}
+
+}  // namespace rowops
+}  // namespace cs
+
+using namespace cs;
+using namespace cs::rowops;
+
+extern "C" const char* cs_last_error(void) { return cs::g_err; }
+extern "C" int cs_abi_version(void) { return 1; }
+
+extern "C" int cs_device_info(int* sm_out, int* num_sms_out, int64_t* hbm_bytes_out) {
+    int dev = 0;
+    CS_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CS_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_out) *sm_out = p.major * 10 + p.minor;
+    if (num_sms_out) *num_sms_out = p.multiProcessorCount;
+    if (hbm_bytes_out) *hbm_bytes_out = (int64_t)p.totalGlobalMem;
+    if (p.major != 10) {
+        set_error("clipself_b200 needs an sm_100 (B200) device, found sm_%d%d", p.major, p.minor);
+        return CS_ERR_UNSUPPORTED;
+    }
+    return CS_OK;
+}
+
+extern "C" int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, int64_t M, int D, int row_div,
+                                int row_mul, int row_off, const float* gamma, const float* beta, float eps,
+                                void* y_bf16, int64_t ldy, float* mean, float* rstd, void* stream) {
+    CS_CHECK_ARG(x && gamma && beta && y_bf16, "cs_layernorm_fwd: null pointer");
+    CS_CHECK_ARG(M > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && row_mul >= 1,
+                 "cs_layernorm_fwd: D, ldx, ldy must be multiples of 8 (D=%d ldx=%lld ldy=%lld)", D, (long long)ldx,
+                 (long long)ldy);
+    const int smem = LN_WARPS * D * (int)sizeof(float);
+    CS_CHECK_ARG(smem <= 160 * 1024, "cs_layernorm_fwd: D=%d too large", D);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ceil_div(M, LN_WARPS);
+    if (x_dtype == CS_F32) {
+        static bool cfg = false;
+        if (!cfg) {
+            CS_CUDA(cudaFuncSetAttribute(layernorm_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            cfg = true;
+        }
+        layernorm_fwd_kernel<float><<<grid, LN_WARPS * 32, smem, st>>>(
+            (const float*)x, ldx, M, D, row_div, row_mul, row_off, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy, mean, rstd);
+    } else {
+        static bool cfg = false;
+        if (!cfg) {
+            CS_CUDA(cudaFuncSetAttribute(layernorm_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            cfg = true;
+        }
+        layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, smem, st>>>(
+            (const __nv_bfloat16*)x, ldx, M, D, row_div, row_mul, row_off, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy, mean, rstd);
+    }
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_im2col_patches(const void* images, cs_dtype_t dtype, int B, int S, int P, void* patches_bf16,
+                                 int64_t ldp, void* stream) {
+    CS_CHECK_ARG(images && patches_bf16, "cs_im2col_patches: null pointer");
+    CS_CHECK_ARG(B > 0 && S > 0 && P > 0 && S % P == 0 && ldp >= 3 * P * P, "cs_im2col_patches: bad shape");
+    dim3 grid(S / P, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CS_F32)
+        im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)images, S, P, (__nv_bfloat16*)patches_bf16, ldp);
+    else
+        im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)images, S, P, (__nv_bfloat16*)patches_bf16, ldp);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_fill_cls_rows(const float* cls_token, const float* pos_embed, int B, int N, int D, float* x,
+                                void* stream) {
+    CS_CHECK_ARG(cls_token && pos_embed && x && B > 0 && N > 0 && D > 0, "cs_fill_cls_rows: bad argument");
+    fill_cls_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cls_token, pos_embed, N, D, x);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_cast_pad_bf16(const float* src, int64_t rows, int64_t cols, int64_t lds, void* dst_bf16,
+                                int64_t ldd, void* stream) {
+    CS_CHECK_ARG(src && dst_bf16 && rows > 0 && cols > 0 && lds >= cols && ldd >= cols, "cs_cast_pad_bf16: bad argument");
+    const long long total = rows * ldd;
+    const int grid = (int)min((long long)num_sms() * 8, (total + 255) / 256);
+    cast_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, lds, (__nv_bfloat16*)dst_bf16, ldd);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_pack_swiglu_weights(const void* w1, const void* w2, cs_dtype_t dtype, int Hd, int K,
+                                      const float* b1, const float* b2, void* packed_bf16, int64_t ldk,
+                                      float* bias12, void* stream) {
+    CS_CHECK_ARG(w1 && w2 && packed_bf16, "cs_pack_swiglu_weights: null pointer");
+    CS_CHECK_ARG(Hd > 0 && K > 0 && ldk >= K && ldk % 8 == 0, "cs_pack_swiglu_weights: bad shape");
+    CS_CHECK_ARG(!bias12 || (b1 && b2), "cs_pack_swiglu_weights: bias12 needs b1 and b2");
+    const int rows = ceil_div(Hd, 128) * 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CS_F32)
+        pack_swiglu_kernel<float><<<rows, 256, 0, st>>>((const float*)w1, (const float*)w2, Hd, K, b1, b2,
+                                                        (__nv_bfloat16*)packed_bf16, ldk, bias12);
+    else
+        pack_swiglu_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>((const __nv_bfloat16*)w1, (const __nv_bfloat16*)w2, Hd, K,
+                                                                b1, b2, (__nv_bfloat16*)packed_bf16, ldk, bias12);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}

@@ -1,0 +1,233 @@
+"""EVA02 vision tower engine: packed weights + kernel sequencing for the CLIPSelf hot path.
+
+Mirrors (reference file:line, wusize/CLIPSelf @ 1c7fe9c):
+  teacher  : EVAVisionTransformer.forward / forward_features   eva_vit_model.py:533-586
+  student  : EVAVisionTransformer.encode_dense                  eva_vit_model.py:588-623
+  blocks   : Block.forward / forward_without_attn               eva_vit_model.py:300-324
+  attention: Attention.forward / proj_without_attn              eva_vit_model.py:174-256
+  mlp      : SwiGLU.forward                                     eva_vit_model.py:98-105
+  rope     : VisionRotaryEmbeddingFast                          rope.py:96-164
+
+Precision contract (the reference's runnable bf16 mode, `--precision amp_bf16`):
+fp32 master weights and residual stream, bf16 tensor-core operands, fp32 accumulation,
+fp32 LayerNorm / softmax / normalise / RoIAlign / loss.
+
+All arithmetic runs in the CUDA library (clipself_b200/csrc); torch only owns the memory.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+Tensor = torch.Tensor
+
+
+@dataclass(frozen=True)
+class TowerCfg:
+    image_size: int = 224
+    patch: int = 16
+    width: int = 768
+    heads: int = 12
+    layers: int = 12
+    hidden: int = 2048
+    embed_dim: int = 512
+    pt_seq_len: int = 16
+    ln_eps: float = 1e-6
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch
+
+    @property
+    def tokens(self) -> int:
+        return self.grid * self.grid + 1
+
+    @property
+    def head_dim(self) -> int:
+        return self.width // self.heads
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def rope_tables(grid: int, head_dim: int, pt_seq_len: int, theta: float = 10000.0):
+    """cos/sin [grid*grid, head_dim] f32, built with the same torch ops / order as rope.py:118-142
+    so the tables are bit-identical to the reference's registered buffers."""
+    dim = head_dim // 2
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    t = torch.arange(grid) / grid * pt_seq_len
+    ang = torch.einsum("..., f -> ... f", t, freqs)
+    ang = ang.repeat_interleave(2, dim=-1)
+    full = torch.cat([ang[:, None, :].expand(grid, grid, dim), ang[None, :, :].expand(grid, grid, dim)], dim=-1)
+    return full.cos().reshape(-1, 2 * dim).contiguous(), full.sin().reshape(-1, 2 * dim).contiguous()
+
+
+class PackedBlock:
+    __slots__ = ("wqkv", "bqkv", "wv", "bv", "wproj", "bproj", "w12", "b12", "w3", "b3",
+                 "g1", "b1", "gi", "bi", "g2", "b2", "gf", "bf")
+
+
+class PackedTower:
+    """GEMM-ready bf16 copies of one tower's weights (rebuilt after every optimizer step for
+    the student, once for the frozen teacher)."""
+
+    def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device):
+        assert cfg.head_dim == 64, "kernels are specialised for head_dim 64 (all EVA02-CLIP configs)"
+        assert cfg.width % 64 == 0 and cfg.embed_dim % 32 == 0
+        assert cfg.hidden % 128 == 0, "hidden must be a multiple of 128 (ViT-L 2730 padding: DESIGN.md roadmap)"
+        self.cfg = cfg
+        self.device = device
+        cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
+        self.rope_cos = cos.to(device)
+        self.rope_sin = sin.to(device)
+        self.k_pe = 3 * cfg.patch * cfg.patch
+        self.k_pe_pad = _round_up(self.k_pe, 8)
+        self.blocks: List[PackedBlock] = [PackedBlock() for _ in range(cfg.layers)]
+        self.repack(sd)
+
+    @staticmethod
+    def _f32(t: Tensor, device) -> Tensor:
+        return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    def repack(self, sd: Dict[str, Tensor]) -> None:
+        cfg, dev = self.cfg, self.device
+        f = lambda k: self._f32(sd[k], dev)  # noqa: E731
+        D = cfg.width
+        self.pe_w = ops.cast_pad_bf16(f("patch_embed.proj.weight").reshape(D, -1), self.k_pe_pad)
+        self.pe_b = f("patch_embed.proj.bias")
+        self.cls = f("cls_token").reshape(-1)
+        self.pos = f("pos_embed").reshape(cfg.tokens, D)
+        self.norm_g, self.norm_b = f("norm.weight"), f("norm.bias")
+        self.head_w = ops.cast_pad_bf16(f("head.weight"))
+        self.head_b = f("head.bias")
+        for i, pb in enumerate(self.blocks):
+            p = f"blocks.{i}."
+            wq, wk, wv = f(p + "attn.q_proj.weight"), f(p + "attn.k_proj.weight"), f(p + "attn.v_proj.weight")
+            pb.wqkv = ops.cast_pad_bf16(torch.cat([wq, wk, wv], dim=0))
+            pb.bqkv = torch.cat([f(p + "attn.q_bias"), torch.zeros(D, device=dev), f(p + "attn.v_bias")])
+            pb.wv = pb.wqkv[2 * D:]
+            pb.bv = pb.bqkv[2 * D:]
+            pb.wproj = ops.cast_pad_bf16(f(p + "attn.proj.weight"))
+            pb.bproj = f(p + "attn.proj.bias")
+            pb.w12, pb.b12 = ops.pack_swiglu_weights(f(p + "mlp.w1.weight"), f(p + "mlp.w2.weight"),
+                                                     f(p + "mlp.w1.bias"), f(p + "mlp.w2.bias"), D)
+            pb.w3 = ops.cast_pad_bf16(f(p + "mlp.w3.weight"))
+            pb.b3 = f(p + "mlp.w3.bias")
+            pb.g1, pb.b1 = f(p + "norm1.weight"), f(p + "norm1.bias")
+            pb.gi, pb.bi = f(p + "attn.inner_attn_ln.weight"), f(p + "attn.inner_attn_ln.bias")
+            pb.g2, pb.b2 = f(p + "norm2.weight"), f(p + "norm2.bias")
+            pb.gf, pb.bf = f(p + "mlp.ffn_ln.weight"), f(p + "mlp.ffn_ln.bias")
+
+
+class Workspace:
+    """Activation scratch for one forward-only chunk of `rows` token rows."""
+
+    def __init__(self, cfg: TowerCfg, rows: int, device):
+        D, Hd = cfg.width, cfg.hidden
+        bf = dict(device=device, dtype=torch.bfloat16)
+        self.rows = rows
+        self.x = torch.empty(rows, D, device=device, dtype=torch.float32)
+        self.u = torch.empty(rows, D, **bf)
+        self.qkv = torch.empty(rows, 3 * D, **bf)
+        self.att = torch.empty(rows, D, **bf)
+        self.h = torch.empty(rows, Hd, **bf)
+        self.h2 = torch.empty(rows, Hd, **bf)
+
+
+class TowerEngine:
+    """Runs the kernel sequence of one tower."""
+
+    def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device, chunk_images: int = 128):
+        L.require_device()
+        self.cfg = cfg
+        self.device = device
+        self.w = PackedTower(cfg, sd, device)
+        self.chunk_images = chunk_images
+        self._ws: Optional[Workspace] = None
+        self.scale = cfg.head_dim ** -0.5
+
+    # ------------------------------------------------------------------ helpers
+    def workspace(self, images: int) -> Workspace:
+        rows = images * self.cfg.tokens
+        if self._ws is None or self._ws.rows < rows:
+            self._ws = Workspace(self.cfg, rows, self.device)
+        return self._ws
+
+    def embed(self, images: Tensor, x: Tensor) -> None:
+        """patch conv as a GEMM + bias + pos_embed, CLS rows (eva_vit_model.py:350-356, 540-544)."""
+        cfg, w = self.cfg, self.w
+        B = images.shape[0]
+        patches = ops.im2col_patches(images, cfg.patch, w.k_pe_pad)
+        ops.gemm(patches, w.pe_w, x, M=B * (cfg.tokens - 1), N=cfg.width, K=w.k_pe_pad, mode=L.EPI_TOKENS,
+                 bias=w.pe_b, pos_embed=w.pos, tokens=cfg.tokens)
+        ops.fill_cls_rows(w.cls, w.pos, x.view(B, cfg.tokens, cfg.width))
+
+    def block_inplace(self, i: int, ws: Workspace, B: int, with_attention: bool = True) -> None:
+        """One residual block on ws.x in place (inference; nothing saved)."""
+        cfg, pb = self.cfg, self.w.blocks[i]
+        D, N = cfg.width, cfg.tokens
+        M = B * N
+        x, u = ws.x, ws.u
+        ops.layernorm_fwd(x, M, D, pb.g1, pb.b1, cfg.ln_eps, u)
+        if with_attention:
+            ops.gemm(u, pb.wqkv, ws.qkv, M=M, mode=L.EPI_QKV_ROPE, bias=pb.bqkv, rope=(self.w.rope_cos, self.w.rope_sin),
+                     tokens=N, rope_cols=2 * D)
+            ops.attention_fwd(ws.qkv, B, N, cfg.heads, self.scale, ws.att)
+        else:
+            ops.gemm(u, pb.wv, ws.att, M=M, bias=pb.bv)
+        ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, cfg.ln_eps, u)
+        ops.gemm(u, pb.wproj, x, M=M, bias=pb.bproj, residual=x)
+        ops.layernorm_fwd(x, M, D, pb.g2, pb.b2, cfg.ln_eps, u)
+        ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12)
+        ops.layernorm_fwd(ws.h, M, cfg.hidden, pb.gf, pb.bf, cfg.ln_eps, ws.h2)
+        ops.gemm(ws.h2, pb.w3, x, M=M, bias=pb.b3, residual=x)
+
+    # ------------------------------------------------------------------ teacher
+    def forward_cls(self, images: Tensor, out: Optional[Tensor] = None) -> Tensor:
+        """encode_image(normalize=False): [R,3,S,S] -> [R, embed_dim] f32, no autograd."""
+        cfg = self.cfg
+        R = images.shape[0]
+        out = out if out is not None else torch.empty(R, cfg.embed_dim, device=self.device, dtype=torch.float32)
+        step = min(self.chunk_images, R)
+        ws = self.workspace(step)
+        cls_ln = torch.empty(step, cfg.width, device=self.device, dtype=torch.bfloat16)
+        for s in range(0, R, step):
+            n = min(step, R - s)
+            self.embed(images[s:s + n], ws.x)
+            for i in range(cfg.layers):
+                self.block_inplace(i, ws, n)
+            ops.layernorm_fwd(ws.x, n, cfg.width, self.w.norm_g, self.w.norm_b, cfg.ln_eps, cls_ln, row_mul=cfg.tokens)
+            ops.gemm(cls_ln, self.w.head_w, out[s:s + n], M=n, bias=self.w.head_b)
+        return out
+
+    # ------------------------------------------------------------------ student (inference)
+    def encode_dense_nograd(self, images: Tensor) -> Tensor:
+        """encode_dense: [B,3,S,S] -> NHWC [B,h,w,C] f32, unit-norm per token (no tape)."""
+        cfg = self.cfg
+        B = images.shape[0]
+        g, C = cfg.grid, cfg.embed_dim
+        out = torch.empty(B, g, g, C, device=self.device, dtype=torch.float32)
+        step = min(self.chunk_images, B)
+        ws = self.workspace(step)
+        for s in range(0, B, step):
+            n = min(step, B - s)
+            self.embed(images[s:s + n], ws.x)
+            for i in range(cfg.layers - 1):
+                self.block_inplace(i, ws, n)
+            self.block_inplace(cfg.layers - 1, ws, n, with_attention=False)
+            Mp = n * g * g
+            tok_ln = ws.u[:Mp]
+            ops.layernorm_fwd(ws.x, Mp, cfg.width, self.w.norm_g, self.w.norm_b, cfg.ln_eps, tok_ln,
+                              row_div=g * g, row_off=1)
+            head = torch.empty(Mp, C, device=self.device, dtype=torch.float32)
+            ops.gemm(tok_ln, self.w.head_w, head, M=Mp, bias=self.w.head_b)
+            y, _ = ops.l2norm_fwd(head)
+            out[s:s + n] = y.view(n, g, g, C)
+        return out

@@ -1,0 +1,174 @@
+/*
+ * clipself_b200 — C ABI of the B200-native CLIPSelf distillation hot path.
+ *
+ * Drop-in boundary for the path  src/training/clipself.py:7-49  of wusize/CLIPSelf and the model
+ * entry points it calls (eva_clip/model.py:313-346, eva_clip/eva_vit_model.py:533-664).
+ * The reference has no native layer (everything is Python -> ATen / torchvision / xformers), so
+ * the "FFI" a maintainer binds is ctypes: see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch's
+ *     caching allocator in our host code) owns all buffers, including outputs and workspaces;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises the device or
+ *     touches a hidden stream; all entry points are re-entrant;
+ *   - return value: 0 (CS_OK) or a CS_ERR_* code; cs_last_error() gives the thread-local text;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - dtype arguments use cs_dtype_t.
+ * All kernels are compiled for sm_100a only; there is no CPU path and no fallback.
+ */
+#ifndef CLIPSELF_B200_H_
+#define CLIPSELF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_OK 0
+#define CS_ERR_INVALID_ARGUMENT 1
+#define CS_ERR_CUDA 2
+#define CS_ERR_UNSUPPORTED 3
+
+typedef enum { CS_F32 = 0, CS_BF16 = 1 } cs_dtype_t;
+
+const char* cs_last_error(void);
+/* Library/ABI version (bumped on any signature change). */
+int cs_abi_version(void);
+/* Fills sm (e.g. 100), SM count, and total HBM bytes of the current device; CS_ERR_CUDA if no
+ * usable sm_100 device is present (the product path must fail loudly, never fall back). */
+int cs_device_info(int* sm_out, int* num_sms_out, int64_t* hbm_bytes_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Region path (HBM-bound, no tensor cores)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Valid-box / crop index extraction — replaces clipself.py:29-36.
+ *   normed_boxes [B,K,5] f32 (x0,y0,x1,y1,valid).  valid := box[4] > 0.5.
+ * Outputs, image-major and order-preserving (bit-exact copies of the inputs):
+ *   rois      [B*K,4] f32  first R rows filled          (== cat(rois_list))
+ *   crop_index[B*K]   i32  flat index b*K+k of each kept row (== index into image_crops.flatten(0,1))
+ *   roi_batch [B*K]   i32  image index of each kept row
+ *   img_offsets[B+1]  i32  exclusive prefix sum of per-image counts; img_offsets[B] == R      */
+int cs_extract_rois(const float* normed_boxes, int B, int K, float* rois, int32_t* crop_index,
+                    int32_t* roi_batch, int32_t* img_offsets, void* stream);
+
+/* Gather rows: dst[r,:] = src[index[r],:], row_bytes % 16 == 0 — the crop gather of
+ * clipself.py:34-36 (torch.cat(crops_list)) when the crops are device resident. */
+int cs_gather_rows(const void* src, const int32_t* index, int R, int64_t row_bytes, void* dst,
+                   void* stream);
+
+/* RoIAlign, output 1x1, spatial_scale 1, sampling_ratio -1 (adaptive), aligned=True, on an NHWC
+ * f32 map — replaces _denormalize_boxes + torchvision.ops.roi_align at eva_vit_model.py:625-629,
+ * 655-664.  rois are the NORMALISED boxes of cs_extract_rois; the x*=W, y*=H denormalisation
+ * happens inside in f32 exactly like the reference.
+ *   fmap [B,H,W,C] f32, out [R,C] f32.  The separable sampling weights are written to
+ *   wy [R,H] / wx [R,W] (f32, caller provided) and reused by the backward. */
+int cs_roi_align_fwd(const float* fmap, int B, int H, int W, int C, const float* rois,
+                     const int32_t* img_offsets, int R, float* wy, float* wx, float* out,
+                     void* stream);
+/* d_fmap [B,H,W,C] f32 is fully overwritten (deterministic gather form, no atomics) —
+ * replaces torchvision's roi_align_backward_kernel. */
+int cs_roi_align_bwd(const float* d_out, int B, int H, int W, int C, const int32_t* img_offsets,
+                     int R, const float* wy, const float* wx, float* d_fmap, void* stream);
+
+/* Mask pooling — replaces EVAVisionTransformer.mask_pool, eva_vit_model.py:645-653, without the
+ * repeat_interleave materialisation.  fmap [B,HW,C] f32, masks [R,HW] f32 (image-major),
+ * out[r] = sum_p f[b(r),p]*m[r,p] / (sum_p m[r,p] + 1e-12). */
+int cs_mask_pool_fwd(const float* fmap, int B, int HW, int C, const float* masks,
+                     const int32_t* img_offsets, int R, float* out, void* stream);
+
+/* L2-normalise + cosine loss — replaces clipself.py:42-47.
+ *   loss = (1 - mean_r <s_r/max(|s_r|,1e-12), t_r/max(|t_r|,1e-12)>) * weight
+ * s,t [R,C] f32; loss: 1 f32; row_stats [R,3] f32 = (1/max|s|, 1/max|t|, cos_r) kept for the
+ * backward; `scratch` >= 4 bytes zero-initialised by the callee (ticket counter). Deterministic
+ * (fixed-order final reduction). */
+int cs_cosine_loss_fwd(const float* s, const float* t, int R, int C, float weight, float* loss,
+                       float* row_stats, void* stream);
+/* d_s [R,C] = d_loss * dloss/ds ; d_loss is a DEVICE scalar (f32). */
+int cs_cosine_loss_bwd(const float* s, const float* t, const float* row_stats, int R, int C,
+                       float weight, const float* d_loss, float* d_s, void* stream);
+
+/* Row-wise L2 normalisation y = x / max(|x|,1e-12) (F.normalize, eva_vit_model.py:620) over
+ * [M,C] f32; inv_norm [M] is saved for the backward. */
+int cs_l2norm_fwd(const float* x, int64_t M, int C, float* y, float* inv_norm, void* stream);
+int cs_l2norm_bwd(const float* y, const float* inv_norm, const float* d_y, int64_t M, int C,
+                  float* d_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tower kernels (EVA02 ViT, eva_vit_model.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Non-overlapping patch gather (im2col of the k=s=P conv, eva_vit_model.py:348-356):
+ *   images [B,3,S,S] (f32 or bf16) -> patches [B*g*g, ldp] bf16, column order (c,py,px) matching
+ *   the flattened conv weight [D, 3*P*P]; columns [3*P*P, ldp) are zero padding. */
+int cs_im2col_patches(const void* images, cs_dtype_t dtype, int B, int S, int P,
+                      void* patches_bf16, int64_t ldp, void* stream);
+
+/* x[b,0,:] = cls_token + pos_embed[0]  (eva_vit_model.py:540-543); x [B,N,D] f32. */
+int cs_fill_cls_rows(const float* cls_token, const float* pos_embed, int B, int N, int D, float* x,
+                     void* stream);
+
+/* LayerNorm forward (eva_clip/transformer.py:52-58, eps from model.py:123), one row per warp.
+ *   x: [*, ldx] f32 or bf16;  logical row m reads physical row  m + (row_div>0 ? m/row_div+row_off : 0)
+ *   (row_div = tokens-1,row_off=1 skips each image's CLS row; row_div=1,row_off... see host code);
+ *   y [M, ldy] bf16;  mean/rstd [M] f32 optional (NULL to skip; needed for backward). */
+int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, int64_t M, int D,
+                     int row_div, int row_mul, int row_off,
+                     const float* gamma, const float* beta, float eps, void* y_bf16, int64_t ldy,
+                     float* mean, float* rstd, void* stream);
+
+/* Epilogue description of cs_gemm_bf16 (all pointers device, may be NULL when unused). */
+typedef enum {
+    CS_EPI_STORE = 0,      /* out = acc + bias (+ residual)                                     */
+    CS_EPI_QKV_ROPE = 1,   /* out(bf16) = rope(acc + bias) on columns < rope_cols, patch rows   */
+    CS_EPI_SWIGLU = 2,     /* out(bf16)[m, n/2-ish] = silu(acc1+b1) * (acc2+b2), gate/up packed */
+    CS_EPI_TOKENS = 3      /* patch-embed: row remap past CLS, + bias + pos_embed               */
+} cs_epilogue_mode_t;
+
+typedef struct {
+    int32_t mode;            /* cs_epilogue_mode_t */
+    int32_t out_dtype;       /* cs_dtype_t */
+    void* out;               /* [M(+), ldo] */
+    int64_t ldo;
+    const float* bias;       /* [N] or NULL */
+    const float* residual;   /* [M, ldr] f32 or NULL; may alias out (in-place x += ...) */
+    int64_t ldr;
+    const float* rope_cos;   /* [tokens-1, 64] f32 */
+    const float* rope_sin;
+    int32_t tokens;          /* tokens per image incl. CLS (QKV_ROPE, TOKENS) */
+    int32_t rope_cols;       /* columns [0, rope_cols) are rotated (= 2*D for q|k|v) */
+    const float* pos_embed;  /* [tokens, N] f32 (TOKENS) */
+    float alpha;             /* scale applied to acc before everything else (1.0 default) */
+    int32_t reserved;
+} cs_gemm_epilogue_t;
+
+/* C[M,N] = A[M,K] · W[N,K]^T on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM ->
+ * epilogue).  A, W bf16 row-major, lda/ldw multiples of 8; K % 8 == 0; N % 32 == 0.
+ * This is the one GEMM behind every F.linear / conv of the tower (eva_vit_model.py:177-179,
+ * 220, 98-105, 355, 569) and their backward products. */
+int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int N, int K,
+                 const cs_gemm_epilogue_t* epi, void* stream);
+
+/* Pack the SwiGLU gate/up weights so that one GEMM tile holds matching x1/x2 columns:
+ *   packed row (t*2*half + j)        = w1 row (t*half + j)
+ *   packed row (t*2*half + half + j) = w2 row (t*half + j),   half = 128, j < half
+ * w1,w2 [Hd, K] f32 or bf16 -> packed [2*Hd_pad, ldk] bf16; biases likewise into bias12 [2*Hd_pad]. */
+int cs_pack_swiglu_weights(const void* w1, const void* w2, cs_dtype_t dtype, int Hd, int K,
+                           const float* b1, const float* b2, void* packed_bf16, int64_t ldk,
+                           float* bias12, void* stream);
+
+/* Non-causal softmax attention over the packed projections (eva_vit_model.py:206-217 / 221-246):
+ *   qkv [B*N, 3*D] bf16 (q | k | v, each H heads of 64, RoPE already applied to q,k),
+ *   out [B*N, D] bf16;  lse [B,H,N] f32 optional (needed for the backward).  head_dim must be 64. */
+int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
+                     float* lse, void* stream);
+
+/* f32 -> bf16 cast of a [rows, cols] matrix into a (possibly wider, zero padded) bf16 matrix. */
+int cs_cast_pad_bf16(const float* src, int64_t rows, int64_t cols, int64_t lds, void* dst_bf16,
+                     int64_t ldd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPSELF_B200_H_ */

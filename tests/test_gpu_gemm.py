@@ -1,0 +1,135 @@
+"""tcgen05 GEMM (cs_gemm_bf16) against a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _report(name, got, ref, tol):
+    err = (got.float() - ref.float()).abs()
+    scale = ref.float().abs().max().item() + 1e-12
+    bad = err > tol * scale
+    msg = f"{name}: max_abs_err={err.max().item():.4e} scale={scale:.3e} bad={bad.float().mean().item():.4f}"
+    if bad.any():
+        M, N = bad.shape
+        bm, bn = max(M // 8, 1), max(N // 8, 1)
+        rows = []
+        for i in range(0, min(M, 8 * bm), bm):
+            rows.append(" ".join(f"{bad[i:i + bm, j:j + bn].float().mean().item():.2f}" for j in range(0, min(N, 8 * bn), bn)))
+        msg += "\n  mismatch-rate map (8x8 blocks over M x N):\n  " + "\n  ".join(rows)
+        idx = bad.nonzero()[:8].tolist()
+        msg += "\n  first bad (m,n,got,ref): " + ", ".join(
+            f"({m},{n},{got[m, n].item():.4f},{ref[m, n].item():.4f})" for m, n in idx)
+    print(msg)
+    return not bad.any(), msg
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from clipself_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda")
+
+
+def _mk(M, N, K, dev, lda=None, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lda = lda or K
+    a = torch.zeros(M, lda, dtype=torch.bfloat16)
+    a[:, :K] = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = torch.zeros(N, lda, dtype=torch.bfloat16)
+    w[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    return a.to(dev), w.to(dev)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 64), (256, 128, 128), (128, 128, 768),
+                                   (1000, 768, 768), (12608, 768, 2048), (3000, 2304, 768),
+                                   (777, 64, 128), (392, 384, 128), (200, 512, 768), (130, 128, 592)])
+def test_gemm_store_f32(dev, M, N, K):
+    from clipself_b200 import ops
+    a, w = _mk(M, N, K, dev, lda=(K + 7) // 8 * 8)
+    out = torch.full((M, N), float("nan"), device=dev)
+    ops.gemm(a, w, out, M=M, N=N, K=K)
+    torch.cuda.synchronize()
+    ref = a[:, :K].float() @ w[:, :K].float().t()
+    ok, msg = _report(f"store_f32 {M}x{N}x{K}", out, ref, 2e-3)
+    assert ok, msg
+
+
+def test_gemm_bias_residual_inplace(dev):
+    from clipself_b200 import ops
+    M, N, K = 1500, 768, 768
+    a, w = _mk(M, N, K, dev, seed=1)
+    bias = torch.randn(N, device=dev)
+    x = torch.randn(M, N, device=dev)
+    ref = x + a.float() @ w.float().t() + bias
+    ops.gemm(a, w, x, bias=bias, residual=x)
+    ok, msg = _report("bias+residual in place", x, ref, 2e-3)
+    assert ok, msg
+
+
+def test_gemm_bf16_out_alpha(dev):
+    from clipself_b200 import ops
+    M, N, K = 900, 1024, 512
+    a, w = _mk(M, N, K, dev, seed=2)
+    bias = torch.randn(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, bias=bias, alpha=0.5)
+    ref = 0.5 * (a.float() @ w.float().t()) + bias
+    ok, msg = _report("bf16 out + alpha", out, ref, 1e-2)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("D,tokens,B", [(768, 197, 5), (128, 17, 9)])
+def test_gemm_qkv_rope(dev, D, tokens, B):
+    from clipself_b200 import ops, _lib as L
+    from clipself_b200.tower import rope_tables
+    M, N, K = B * tokens, 3 * D, D
+    a, w = _mk(M, N, K, dev, seed=3)
+    bias = torch.randn(N, device=dev)
+    g = int((tokens - 1) ** 0.5)
+    cos, sin = rope_tables(g, 64, 16)
+    cos, sin = cos.to(dev), sin.to(dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, mode=L.EPI_QKV_ROPE, bias=bias, rope=(cos, sin), tokens=tokens, rope_cols=2 * D)
+    y = (a.float() @ w.float().t() + bias).view(B, tokens, 3, D // 64, 64)
+    ref = y.clone()
+    t = y[:, 1:, :2]                                   # patch tokens, q and k
+    pairs = t.reshape(*t.shape[:-1], 32, 2)
+    rot = torch.stack((-pairs[..., 1], pairs[..., 0]), -1).reshape(t.shape)
+    ref[:, 1:, :2] = t * cos[None, :, None, None, :] + rot * sin[None, :, None, None, :]
+    ok, msg = _report("qkv+rope", out, ref.view(M, N), 1e-2)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("D,Hd,M", [(768, 2048, 1000), (128, 384, 300)])
+def test_gemm_swiglu(dev, D, Hd, M):
+    from clipself_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(4)
+    w1 = (torch.randn(Hd, D, generator=g) / D ** 0.5).to(dev)
+    w2 = (torch.randn(Hd, D, generator=g) / D ** 0.5).to(dev)
+    b1 = torch.randn(Hd, generator=g).to(dev)
+    b2 = torch.randn(Hd, generator=g).to(dev)
+    a = torch.randn(M, D, generator=g).to(torch.bfloat16).to(dev)
+    packed, b12 = ops.pack_swiglu_weights(w1, w2, b1, b2, D)
+    out = torch.empty(M, Hd, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, packed, out, mode=L.EPI_SWIGLU, bias=b12)
+    x1 = a.float() @ w1.to(torch.bfloat16).float().t() + b1
+    x2 = a.float() @ w2.to(torch.bfloat16).float().t() + b2
+    ref = torch.nn.functional.silu(x1) * x2
+    ok, msg = _report("swiglu", out, ref, 1e-2)
+    assert ok, msg
+
+
+def test_gemm_tokens(dev):
+    from clipself_b200 import ops, _lib as L
+    B, tokens, D, K = 3, 197, 768, 768
+    M = B * (tokens - 1)
+    a, w = _mk(M, D, K, dev, seed=5)
+    bias = torch.randn(D, device=dev)
+    pos = torch.randn(tokens, D, device=dev)
+    x = torch.zeros(B * tokens, D, device=dev)
+    ops.gemm(a, w, x, M=M, mode=L.EPI_TOKENS, bias=bias, pos_embed=pos, tokens=tokens)
+    ref = torch.zeros(B, tokens, D, device=dev)
+    ref[:, 1:] = (a.float() @ w.float().t() + bias).view(B, tokens - 1, D) + pos[1:]
+    ok, msg = _report("tokens", x, ref.view(B * tokens, D), 2e-3)
+    assert ok, msg

@@ -1,0 +1,112 @@
+"""Region-path kernels (index extraction bit-exact; RoIAlign / mask pool / loss against the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clipself_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from clipself_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda")
+
+
+@pytest.mark.parametrize("B,K,ragged", [(4, 6, True), (64, 32, False), (3, 1, True), (129, 20, True)])
+def test_extract_rois_bit_exact(dev, B, K, ragged):
+    from clipself_b200 import ops
+    _, boxes, _ = O.synth_batch(O.CFG_TINY, B, K, 11, kind="proposal", ragged=ragged, crop_size=16)
+    rois_ref, idx_ref = O.extract_rois(boxes)
+    rois, crop_index, roi_batch, offsets = ops.extract_rois(boxes.to(dev))
+    R = int(offsets[-1])
+    assert R == idx_ref.numel()
+    assert torch.equal(rois[:R].cpu(), torch.cat(rois_ref))            # bit-exact
+    assert crop_index[:R].cpu().tolist() == idx_ref.tolist()
+    counts = [r.shape[0] for r in rois_ref]
+    assert offsets.cpu().tolist() == [0] + list(np.cumsum(counts))
+    assert roi_batch[:R].cpu().tolist() == [b for b, c in enumerate(counts) for _ in range(c)]
+
+
+def test_extract_rois_all_invalid(dev):
+    from clipself_b200 import ops
+    boxes = torch.zeros(2, 3, 5, device=dev)
+    *_, offsets = ops.extract_rois(boxes)
+    assert offsets.cpu().tolist() == [0, 0, 0]
+
+
+def test_gather_rows(dev):
+    from clipself_b200 import ops
+    src = torch.randn(10, 3, 8, 8, device=dev)
+    idx = torch.tensor([7, 0, 3, 3], device=dev, dtype=torch.int32)
+    assert torch.equal(ops.gather_rows(src, idx, 4), src[idx.long()])
+
+
+@pytest.mark.parametrize("B,H,W,C,K,kind", [(2, 14, 14, 512, 8, "grid"), (3, 4, 4, 64, 5, "proposal"),
+                                            (2, 24, 24, 768, 6, "proposal"), (2, 7, 9, 96, 4, "proposal")])
+def test_roi_align_fwd_bwd(dev, B, H, W, C, K, kind):
+    from clipself_b200 import ops
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(0)
+    fmap = torch.randn(B, H, W, C)
+    _, boxes, _ = O.synth_batch(O.CFG_TINY, B, K, 5, kind=kind, ragged=(kind == "proposal"), crop_size=16)
+    boxes[0, 0, :4] = torch.tensor([0.0, 0.0, 1.0, 1.0])           # whole image
+    boxes[-1, 0, :4] = torch.tensor([0.93, 0.9, 1.0, 1.0])         # touches the far edge
+    rois, _, _, offsets = ops.extract_rois(boxes.to(dev))
+    R = int(offsets[-1])
+    out, wy, wx = ops.roi_align_fwd(fmap.to(dev), rois, offsets, R)
+    rois_list, _ = O.extract_rois(boxes)
+    den = O.denormalize_boxes(rois_list, H, W)
+    fm = fmap.clone().requires_grad_(True)
+    ref = tv.ops.roi_align(fm.permute(0, 3, 1, 2), den, (1, 1), 1.0, -1, True)[..., 0, 0]
+    np.testing.assert_allclose(out.cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=2e-6)
+    if R <= 12:
+        np.testing.assert_allclose(out.cpu().numpy(), O.roi_align_1x1_nhwc(fmap, den).numpy(), rtol=1e-4, atol=2e-6)
+    d_out = torch.randn(R, C)
+    ref.backward(d_out)
+    d_fmap = ops.roi_align_bwd(d_out.to(dev), (B, H, W, C), offsets, R, wy, wx)
+    np.testing.assert_allclose(d_fmap.cpu().numpy(), fm.grad.numpy(), rtol=1e-4, atol=2e-6)
+
+
+def test_mask_pool(dev):
+    from clipself_b200 import ops
+    torch.manual_seed(1)
+    B, h, w, C = 3, 6, 6, 128
+    fmap = torch.nn.functional.normalize(torch.randn(B, h, w, C), dim=-1)
+    masks = [(torch.rand(n, h, w) > 0.6).float() for n in (2, 0, 3)]
+    ref = O.mask_pool(fmap, masks)
+    offsets = torch.tensor([0, 2, 2, 5], dtype=torch.int32, device=dev)
+    out = ops.mask_pool_fwd(fmap.view(B, h * w, C).to(dev), torch.cat(masks).flatten(1).to(dev), offsets)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("R,C", [(16, 512), (2048, 512), (37, 64), (1, 768)])
+def test_cosine_loss_fwd_bwd(dev, R, C):
+    from clipself_b200 import ops
+    torch.manual_seed(2)
+    s = torch.randn(R, C, requires_grad=True)
+    t = torch.randn(R, C) * 3
+    ref = O.cosine_loss(s, t, 0.7)
+    ref.backward(torch.tensor(1.3))
+    loss, stats = ops.cosine_loss_fwd(s.detach().to(dev), t.to(dev), 0.7)
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-6, atol=1e-6)
+    d_s = ops.cosine_loss_bwd(s.detach().to(dev), t.to(dev), stats, 0.7, torch.tensor(1.3, device=dev))
+    np.testing.assert_allclose(d_s.cpu().numpy(), s.grad.numpy(), rtol=1e-4, atol=1e-8)
+    # determinism (fixed-order reduction)
+    loss2, _ = ops.cosine_loss_fwd(s.detach().to(dev), t.to(dev), 0.7)
+    assert loss2.item() == loss.item()
+
+
+def test_l2norm_fwd_bwd(dev):
+    from clipself_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(777, 512, requires_grad=True)
+    y_ref = torch.nn.functional.normalize(x, dim=-1)
+    g = torch.randn(777, 512)
+    y_ref.backward(g)
+    y, inv = ops.l2norm_fwd(x.detach().to(dev))
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref.detach().numpy(), rtol=1e-5, atol=1e-7)
+    dx = ops.l2norm_bwd(y, inv, g.to(dev))
+    np.testing.assert_allclose(dx.cpu().numpy(), x.grad.numpy(), rtol=1e-4, atol=1e-6)

@@ -1,0 +1,48 @@
+"""Tower forward on the GPU against the reference's golden outputs and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clipself_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(o):
+    from clipself_b200.tower import TowerCfg
+    return TowerCfg(image_size=o.image_size, patch=o.patch, width=o.width, heads=o.heads, layers=o.layers,
+                    hidden=o.hidden, embed_dim=o.embed_dim, pt_seq_len=o.pt_seq_len, ln_eps=o.ln_eps)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+CASES = {"tiny_ragged": (O.CFG_TINY, 3, 5, "proposal", True), "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
+         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False)}
+
+
+@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_grid", "cfg1_b16"])
+def test_tower_forward_vs_golden(golden, tag):
+    """bf16 tensor-core path vs the reference's fp32 outputs.  Tolerance: rel-L2 <= 1.5e-2 on
+    feature maps (the reference's own bf16-autocast deviation is stored in the fixture as the
+    yardstick: ours must not be worse than 1.5x theirs + 2e-3)."""
+    from clipself_b200.tower import TowerEngine
+    ocfg, B, K, kind, ragged = CASES[tag]
+    g = golden(tag)
+    seed = int(g["seed"])
+    dev = torch.device("cuda")
+    images, boxes, crops = O.synth_batch(ocfg, B, K, seed + 2, kind=kind, ragged=ragged)
+    cfg = _cfg(ocfg)
+    student = TowerEngine(cfg, O.synth_tower_weights(ocfg, seed), dev)
+    teacher = TowerEngine(cfg, O.synth_tower_weights(ocfg, seed + 1), dev)
+    _, idx = O.extract_rois(boxes)
+    tc = crops.flatten(0, 1)[idx].to(dev)
+    t = teacher.forward_cls(tc).cpu().numpy()
+    d = student.encode_dense_nograd(images.to(dev)).cpu().numpy()
+    yard = float(g["ref_autocast_bf16_dense_rel_l2"])
+    rt, rd = _rel(t, g["teacher"]), _rel(d, g["dense_nhwc"])
+    print(f"{tag}: teacher rel-L2 {rt:.3e}  dense rel-L2 {rd:.3e}  (reference bf16-autocast dense yardstick {yard:.3e})")
+    assert rd <= 1.5 * yard + 2e-3
+    assert rt <= 2.5e-2
