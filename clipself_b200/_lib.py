@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libclipself_b200.so")
 CS_F32, CS_BF16 = 0, 1
 EPI_STORE, EPI_QKV_ROPE, EPI_SWIGLU, EPI_TOKENS = 0, 1, 2, 3
 
-vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 
 class GemmEpilogue(C.Structure):
@@ -45,6 +45,14 @@ PROTOTYPES = {
     "cs_pack_swiglu_weights": [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp],
     "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp],
     "cs_cast_pad_bf16": [vp, i64, i64, i64, vp, i64, vp],
+    "cs_attention_bwd": [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp],
+    "cs_cast_transpose_bf16": [vp, i32, i64, i32, i64, vp, i64, vp, i64, vp],
+    "cs_layernorm_bwd_dx": [vp, i32, i64, vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, i32,
+                            i64, i32, vp],
+    "cs_col_reduce": [vp, i32, i64, vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp],
+    "cs_swiglu_fwd": [vp, i64, i32, i64, vp, i64, i32, vp],
+    "cs_swiglu_bwd": [vp, vp, i64, i32, i64, i64, vp, i32, vp],
+    "cs_adamw_step": [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, f64, vp],
 }
 
 _lib = None

@@ -120,16 +120,26 @@ __global__ void col_reduce_kernel(const float* __restrict__ partial, int S, int 
 // SwiGLU on the packed layout of cs_pack_swiglu_weights: hidden column j = t*128 + jj has its gate
 // at packed column t*256 + jj and its up value at t*256 + 128 + jj.
 // --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void swiglu_cols(int j, int Hd, int split, int& gate_col, int& up_col) {
+    if (split) {
+        gate_col = j;
+        up_col = Hd + j;
+    } else {
+        gate_col = (j >> 7) * 256 + (j & 127);
+        up_col = gate_col + 128;
+    }
+}
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x12, long long M, int Hd, long long ld12,
-                                  __nv_bfloat16* __restrict__ h, long long ldh) {
+                                  __nv_bfloat16* __restrict__ h, long long ldh, int split) {
     const long long total = M * (Hd / 2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / (Hd / 2);
         const int j = (int)(i % (Hd / 2)) * 2;
-        const int pc = (j >> 7) * 256 + (j & 127);
+        int pc, uc;
+        swiglu_cols(j, Hd, split, pc, uc);
         const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(x12 + m * ld12 + pc));
-        const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(x12 + m * ld12 + pc + 128));
+        const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(x12 + m * ld12 + uc));
         const float h0 = g.x / (1.f + __expf(-g.x)) * u.x;
         const float h1 = g.y / (1.f + __expf(-g.y)) * u.y;
         *reinterpret_cast<uint32_t*>(h + m * ldh + j) = pack_bf16(h0, h1);
@@ -137,22 +147,23 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x12, long lo
 }
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const __nv_bfloat16* __restrict__ dh,
                                   long long M, int Hd, long long ld12, long long lddh,
-                                  __nv_bfloat16* __restrict__ dx12) {
+                                  __nv_bfloat16* __restrict__ dx12, int split) {
     const long long total = M * (Hd / 2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / (Hd / 2);
         const int j = (int)(i % (Hd / 2)) * 2;
-        const int pc = (j >> 7) * 256 + (j & 127);
+        int pc, uc;
+        swiglu_cols(j, Hd, split, pc, uc);
         const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(x12 + m * ld12 + pc));
-        const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(x12 + m * ld12 + pc + 128));
+        const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(x12 + m * ld12 + uc));
         const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dh + m * lddh + j));
         const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
         const float dg0 = d.x * u.x * s0 * (1.f + g.x * (1.f - s0));
         const float dg1 = d.y * u.y * s1 * (1.f + g.y * (1.f - s1));
         const float du0 = d.x * g.x * s0, du1 = d.y * g.y * s1;
         *reinterpret_cast<uint32_t*>(dx12 + m * ld12 + pc) = pack_bf16(dg0, dg1);
-        *reinterpret_cast<uint32_t*>(dx12 + m * ld12 + pc + 128) = pack_bf16(du0, du1);
+        *reinterpret_cast<uint32_t*>(dx12 + m * ld12 + uc) = pack_bf16(du0, du1);
     }
 }
 
@@ -255,39 +266,44 @@ extern "C" int cs_col_reduce(const void* dy, cs_dtype_t dy_dtype, int64_t lddy, 
 }
 
 extern "C" int cs_swiglu_fwd(const void* x12_bf16, int64_t M, int Hd, int64_t ld12, void* h_bf16, int64_t ldh,
-                             void* stream) {
-    CS_CHECK_ARG(x12_bf16 && h_bf16 && M > 0 && Hd > 0 && Hd % 128 == 0 && ld12 >= 2 * Hd && ldh >= Hd,
-                 "cs_swiglu_fwd: bad argument (Hd must be a multiple of 128)");
+                             int split_layout, void* stream) {
+    CS_CHECK_ARG(x12_bf16 && h_bf16 && M > 0 && Hd > 0 && Hd % 2 == 0 && ld12 >= 2 * Hd && ldh >= Hd &&
+                     (split_layout || Hd % 128 == 0),
+                 "cs_swiglu_fwd: bad argument (packed layout needs Hd %% 128 == 0)");
     const long long total = M * (Hd / 2);
     const int grid = (int)(((total + 255) / 256) < (long long)num_sms() * 16 ? ((total + 255) / 256) : (long long)num_sms() * 16);
     swiglu_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x12_bf16, M, Hd, ld12,
-                                                              (__nv_bfloat16*)h_bf16, ldh);
+                                                              (__nv_bfloat16*)h_bf16, ldh, split_layout);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
 extern "C" int cs_swiglu_bwd(const void* x12_bf16, const void* dh_bf16, int64_t M, int Hd, int64_t ld12,
-                             int64_t lddh, void* dx12_bf16, void* stream) {
-    CS_CHECK_ARG(x12_bf16 && dh_bf16 && dx12_bf16 && M > 0 && Hd > 0 && Hd % 128 == 0 && ld12 >= 2 * Hd && lddh >= Hd,
+                             int64_t lddh, void* dx12_bf16, int split_layout, void* stream) {
+    CS_CHECK_ARG(x12_bf16 && dh_bf16 && dx12_bf16 && M > 0 && Hd > 0 && Hd % 2 == 0 && ld12 >= 2 * Hd && lddh >= Hd &&
+                     (split_layout || Hd % 128 == 0),
                  "cs_swiglu_bwd: bad argument");
     const long long total = M * (Hd / 2);
     const int grid = (int)(((total + 255) / 256) < (long long)num_sms() * 16 ? ((total + 255) / 256) : (long long)num_sms() * 16);
     swiglu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x12_bf16,
                                                               (const __nv_bfloat16*)dh_bf16, M, Hd, ld12, lddh,
-                                                              (__nv_bfloat16*)dx12_bf16);
+                                                              (__nv_bfloat16*)dx12_bf16, split_layout);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
-extern "C" int cs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                             float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                             void* stream) {
+extern "C" int cs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                             double beta1, double beta2, double eps, double weight_decay, int step,
+                             double grad_scale, void* stream) {
     CS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "cs_adamw_step: bad argument");
-    const float bc1 = 1.f - powf(beta1, (float)step);
-    const float bc2 = 1.f - powf(beta2, (float)step);
-    const int grid = (int)(((n + 255) / 256) < (long long)num_sms() * 16 ? ((n + 255) / 256) : (long long)num_sms() * 16);
-    adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                         weight_decay, bc1, sqrtf(bc2), grad_scale);
+    // bias corrections in double like torch.optim (python floats)
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    const long long blocks = (n + 255) / 256;
+    const int grid = (int)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
+    adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)lr, (float)beta1,
+                                                         (float)beta2, (float)eps, (float)weight_decay, (float)bc1,
+                                                         (float)sqrt(bc2), (float)grad_scale);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

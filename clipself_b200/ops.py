@@ -202,3 +202,54 @@ def cast_pad_bf16(src: Tensor, ldd: Optional[int] = None) -> Tensor:
     out = torch.empty(rows, ldd, device=src.device, dtype=torch.bfloat16)
     call("cs_cast_pad_bf16", _p(src2), rows, cols, cols, _p(out), ldd, _stream())
     return out
+
+
+# ------------------------------------------------------------------ backward kernels
+def attention_bwd(qkv: Tensor, out: Tensor, d_out: Tensor, lse: Tensor, B: int, N: int, H: int, scale: float,
+                  rope: Optional[Tuple[Tensor, Tensor]], delta_ws: Tensor, dqkv: Tensor) -> Tensor:
+    call("cs_attention_bwd", _p(qkv), _p(out), _p(d_out), _p(lse), B, N, H, float(scale),
+         _p(rope[0]) if rope else None, _p(rope[1]) if rope else None, _p(delta_ws), _p(dqkv), _stream())
+    return dqkv
+
+
+def cast_transpose(src: Tensor, M: int, N: int, dst: Optional[Tensor] = None, dst_t: Optional[Tensor] = None,
+                   lds: Optional[int] = None) -> None:
+    """src [M,N] (f32|bf16) -> dst [M,*] bf16 and/or dst_t [N,*] bf16."""
+    call("cs_cast_transpose_bf16", _p(src), _dt(src), M, N, lds if lds is not None else src.shape[-1],
+         _p(dst), dst.shape[-1] if dst is not None else 0, _p(dst_t), dst_t.shape[-1] if dst_t is not None else 0,
+         _stream())
+
+
+def layernorm_bwd_dx(dy: Tensor, x: Tensor, M: int, D: int, mean: Tensor, rstd: Tensor, gamma: Tensor, dx: Tensor,
+                     add: Optional[Tensor] = None, row_div: int = 0, row_mul: int = 1, row_off: int = 0,
+                     row_mapped: bool = False) -> Tensor:
+    call("cs_layernorm_bwd_dx", _p(dy), _dt(dy), dy.shape[-1], _p(x), _dt(x), x.shape[-1], M, D, row_div, row_mul,
+         row_off, _p(mean), _p(rstd), _p(gamma), _p(add), add.shape[-1] if add is not None else 0, _p(dx), _dt(dx),
+         dx.shape[-1], int(row_mapped), _stream())
+    return dx
+
+
+def col_reduce(dy: Tensor, M: int, D: int, dbeta: Tensor, workspace: Tensor, x: Optional[Tensor] = None,
+               mean: Optional[Tensor] = None, rstd: Optional[Tensor] = None, dgamma: Optional[Tensor] = None,
+               row_div: int = 0, row_mul: int = 1, row_off: int = 0, lddy: Optional[int] = None) -> None:
+    call("cs_col_reduce", _p(dy), _dt(dy), lddy if lddy is not None else dy.shape[-1], _p(x),
+         _dt(x) if x is not None else 0, x.shape[-1] if x is not None else 0, M, D, row_div, row_mul, row_off,
+         _p(mean), _p(rstd), _p(dgamma), _p(dbeta), _p(workspace), workspace.numel(), _stream())
+
+
+def swiglu_fwd(x12: Tensor, M: int, Hd: int, h: Tensor, split: bool = True) -> Tensor:
+    call("cs_swiglu_fwd", _p(x12), M, Hd, x12.shape[-1], _p(h), h.shape[-1], int(split), _stream())
+    return h
+
+
+def swiglu_bwd(x12: Tensor, dh: Tensor, M: int, Hd: int, dx12: Tensor, split: bool = True) -> Tensor:
+    call("cs_swiglu_bwd", _p(x12), _p(dh), M, Hd, x12.shape[-1], dh.shape[-1], _p(dx12), int(split), _stream())
+    return dx12
+
+
+def adamw_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float,
+               beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    call("cs_adamw_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, float(lr), float(beta1), float(beta2),
+         float(eps), float(weight_decay), int(step), float(grad_scale), _stream())

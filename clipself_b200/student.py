@@ -1,0 +1,373 @@
+"""Student (trainable) tower: flat parameter / gradient buffers, taped forward, hand-written backward.
+
+Reference semantics being reproduced (wusize/CLIPSelf @ 1c7fe9c):
+  forward   EVAVisionTransformer.encode_dense            eva_vit_model.py:588-623
+  backward  torch autograd through the above, for the parameters left trainable by
+            EVAVisionTransformer.lock(unlocked_groups=depth)        eva_vit_model.py:500-516
+            (all of visual.blocks.*; the last block's q_proj/k_proj/q_bias never receive a
+            gradient because forward_without_attn skips them, eva_vit_model.py:249-256, 317-324)
+  grad sync one mean all-reduce over the flat gradient buffer (what DDP at main.py:188 is meant to do;
+            SURVEY.md fact 7) — issued by the caller (training/clipself.py) on `flat_grad[:n_grad]`.
+
+Memory layout (HBM, all f32, one allocation each for params / grads / Adam moments):
+  [ 2-D weights of every block, in GEMM-friendly groups | 1-D vectors | grad-less tail ]
+   \__ weight-decay group (main.py:199-213) _________/ \_ no-decay _/ \_ never updated _/
+  q|k|v weights of a block are adjacent ([3D,D] view = fused QKV operand and its wgrad output),
+  w1|w2 likewise ([2Hd,D]).  The wgrad GEMMs and bias/LN column reductions write straight into
+  the flat gradient buffer: no per-tensor copies, one all-reduce, two AdamW launches.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .tower import PackedTower, TowerCfg, _round_up
+
+Tensor = torch.Tensor
+
+W_NAMES = ["attn.q_proj.weight", "attn.k_proj.weight", "attn.v_proj.weight", "attn.proj.weight",
+           "mlp.w1.weight", "mlp.w2.weight", "mlp.w3.weight"]
+V_NAMES = ["norm1.weight", "norm1.bias", "attn.q_bias", "attn.v_bias", "attn.inner_attn_ln.weight",
+           "attn.inner_attn_ln.bias", "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.w1.bias",
+           "mlp.w2.bias", "mlp.ffn_ln.weight", "mlp.ffn_ln.bias", "mlp.w3.bias"]
+GRADLESS_LAST = ("attn.q_proj.weight", "attn.k_proj.weight", "attn.q_bias")
+
+
+def block_param_shape(cfg: TowerCfg, name: str) -> Tuple[int, ...]:
+    D, Hd = cfg.width, cfg.hidden
+    if name in ("mlp.w1.weight", "mlp.w2.weight"):
+        return (Hd, D)
+    if name == "mlp.w3.weight":
+        return (D, Hd)
+    if name.endswith("proj.weight"):
+        return (D, D)
+    if name in ("mlp.w1.bias", "mlp.w2.bias", "mlp.ffn_ln.weight", "mlp.ffn_ln.bias"):
+        return (Hd,)
+    return (D,)
+
+
+class FlatLayout:
+    """Offsets (in elements) of every `blocks.*` parameter inside the flat buffer."""
+
+    def __init__(self, cfg: TowerCfg):
+        self.cfg = cfg
+        self.offset: Dict[str, int] = {}
+        self.shape: Dict[str, Tuple[int, ...]] = {}
+        last = cfg.layers - 1
+        off = 0
+        tail: List[str] = []
+
+        def place(full: str, shape):
+            nonlocal off
+            self.offset[full] = off
+            self.shape[full] = shape
+            n = 1
+            for s in shape:
+                n *= s
+            off += n
+
+        for i in range(cfg.layers):
+            for nm in W_NAMES:
+                full = f"blocks.{i}.{nm}"
+                if i == last and nm in GRADLESS_LAST:
+                    tail.append(full)
+                else:
+                    place(full, block_param_shape(cfg, nm))
+        self.n_decay = off                      # [0, n_decay): 2-D weights, weight-decay group
+        for i in range(cfg.layers):
+            for nm in V_NAMES:
+                full = f"blocks.{i}.{nm}"
+                if i == last and nm in GRADLESS_LAST:
+                    tail.append(full)
+                else:
+                    place(full, block_param_shape(cfg, nm))
+        self.n_grad = off                       # [n_decay, n_grad): vectors, no-decay group
+        for full in tail:
+            nm = full.split(".", 2)[2]
+            place(full, block_param_shape(cfg, nm))
+        self.n_total = off                      # [n_grad, n_total): parameters that never get a gradient
+        self.gradless = tuple(tail)
+
+    def view(self, flat: Tensor, name: str) -> Tensor:
+        o = self.offset[name]
+        shape = self.shape[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return flat[o:o + n].view(shape)
+
+    def names(self) -> List[str]:
+        return list(self.offset.keys())
+
+
+class _BlockPack:
+    __slots__ = ("wqkv", "wqkvT", "bqkv", "wv", "wvT", "wproj", "wprojT", "w12", "w12T", "w3", "w3T")
+
+
+class _Tape:
+    """Saved activations of one student forward (allocated once per batch size)."""
+
+    def __init__(self, cfg: TowerCfg, B: int, dev):
+        D, Hd, N, H, Lr = cfg.width, cfg.hidden, cfg.tokens, cfg.heads, cfg.layers
+        M = B * N
+        Mp = B * (N - 1)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.B, self.M, self.Mp = B, M, Mp
+        self.x = [torch.empty(M, D, **f32) for _ in range(Lr + 1)]
+        self.xmid = [torch.empty(M, D, **f32) for _ in range(Lr)]
+        self.u = [torch.empty(M, D, **bf) for _ in range(Lr)]
+        self.qkv = [torch.empty(M, 3 * D, **bf) if i < Lr - 1 else None for i in range(Lr)]
+        self.att = [torch.empty(M, D, **bf) for _ in range(Lr)]
+        self.lse = [torch.empty(B, H, N, **f32) if i < Lr - 1 else None for i in range(Lr)]
+        self.aln = [torch.empty(M, D, **bf) for _ in range(Lr)]
+        self.u2 = [torch.empty(M, D, **bf) for _ in range(Lr)]
+        self.x12 = [torch.empty(M, 2 * Hd, **bf) for _ in range(Lr)]
+        self.h = [torch.empty(M, Hd, **bf) for _ in range(Lr)]
+        self.hln = [torch.empty(M, Hd, **bf) for _ in range(Lr)]
+        self.stats = [[torch.empty(M, **f32) for _ in range(8)] for _ in range(Lr)]   # mean/rstd x 4 LNs
+        self.tok_ln = torch.empty(Mp, D, **bf)
+        self.tok_stats = [torch.empty(Mp, **f32) for _ in range(2)]
+        self.head = torch.empty(Mp, cfg.embed_dim, **f32)
+        self.dense = torch.empty(Mp, cfg.embed_dim, **f32)
+        self.inv_norm = torch.empty(Mp, **f32)
+        # backward scratch
+        Mpad = _round_up(M, 8)
+        self.Mpad = Mpad
+        self.dx = torch.empty(M, D, **f32)
+        self.g_bf_D = torch.empty(M, D, **bf)            # bf16 copy of a [M,D] gradient
+        self.g_T_D = torch.empty(D, Mpad, **bf)          # and its transpose
+        self.act_T_D = torch.empty(D, Mpad, **bf)        # transpose of a saved [M,D] activation
+        self.g_Hd = torch.empty(M, Hd, **bf)
+        self.g_Hd2 = torch.empty(M, Hd, **bf)
+        self.act_T_Hd = torch.empty(Hd, Mpad, **bf)
+        self.g_2Hd = torch.empty(M, 2 * Hd, **bf)
+        self.g_T_2Hd = torch.empty(2 * Hd, Mpad, **bf)
+        self.g_3D = torch.empty(M, 3 * D, **bf)
+        self.g_T_3D = torch.empty(3 * D, Mpad, **bf)
+        self.g_D2 = torch.empty(M, D, **bf)
+        self.delta = torch.empty(B * H * N, **f32)
+        self.d_head = torch.empty(Mp, cfg.embed_dim, **f32)
+        self.d_head_bf = torch.empty(Mp, cfg.embed_dim, **bf)
+        self.col_ws = torch.empty(128 * 2 * max(3 * D, 2 * Hd), **f32)
+
+
+class StudentEngine:
+    """Owns the flat f32 parameter / gradient buffers of `visual.blocks.*` and runs the taped
+    forward and the backward of the dense path."""
+
+    def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device):
+        L.require_device()
+        assert cfg.hidden % 128 == 0 and cfg.head_dim == 64
+        self.cfg, self.device = cfg, device
+        self.layout = FlatLayout(cfg)
+        lay = self.layout
+        self.flat_param = torch.empty(lay.n_total, device=device, dtype=torch.float32)
+        self.flat_grad = torch.zeros(lay.n_total, device=device, dtype=torch.float32)
+        for name in lay.names():
+            lay.view(self.flat_param, name).copy_(sd[name].detach().to(device=device, dtype=torch.float32))
+        # frozen parts (patch embed, cls, pos, final norm, head): the generic packer handles them
+        self.frozen = PackedTower.__new__(PackedTower)
+        self._pack_frozen(sd)
+        self.packs = [_BlockPack() for _ in range(cfg.layers)]
+        self._alloc_packs()
+        self.scale = cfg.head_dim ** -0.5
+        self._tape: Optional[_Tape] = None
+        self.repack()
+
+    # ------------------------------------------------------------------ packing
+    def _pack_frozen(self, sd):
+        cfg, dev = self.cfg, self.device
+        f = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        fr = self.frozen
+        from .tower import rope_tables
+        cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
+        fr.rope_cos, fr.rope_sin = cos.to(dev), sin.to(dev)
+        fr.k_pe = 3 * cfg.patch * cfg.patch
+        fr.k_pe_pad = _round_up(fr.k_pe, 8)
+        D = cfg.width
+        fr.pe_w = ops.cast_pad_bf16(f("patch_embed.proj.weight").reshape(D, -1), fr.k_pe_pad)
+        fr.pe_b = f("patch_embed.proj.bias")
+        fr.cls = f("cls_token").reshape(-1)
+        fr.pos = f("pos_embed").reshape(cfg.tokens, D)
+        fr.norm_g, fr.norm_b = f("norm.weight"), f("norm.bias")
+        hw = f("head.weight")
+        fr.head_w = torch.empty(cfg.embed_dim, D, device=dev, dtype=torch.bfloat16)
+        self.head_wT = torch.empty(D, cfg.embed_dim, device=dev, dtype=torch.bfloat16)
+        ops.cast_transpose(hw, cfg.embed_dim, D, dst=fr.head_w, dst_t=self.head_wT)
+        fr.head_b = f("head.bias")
+
+    def _alloc_packs(self):
+        cfg, dev = self.cfg, self.device
+        D, Hd = cfg.width, cfg.hidden
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        for i, pk in enumerate(self.packs):
+            last = i == cfg.layers - 1
+            if not last:
+                pk.wqkv = torch.empty(3 * D, D, **bf)
+                pk.wqkvT = torch.empty(D, 3 * D, **bf)
+                pk.bqkv = torch.zeros(3 * D, device=dev, dtype=torch.float32)
+                pk.wv = pk.wvT = None
+            else:
+                pk.wqkv = pk.wqkvT = pk.bqkv = None
+                pk.wv = torch.empty(D, D, **bf)
+                pk.wvT = torch.empty(D, D, **bf)
+            pk.wproj = torch.empty(D, D, **bf)
+            pk.wprojT = torch.empty(D, D, **bf)
+            pk.w12 = torch.empty(2 * Hd, D, **bf)
+            pk.w12T = torch.empty(D, 2 * Hd, **bf)
+            pk.w3 = torch.empty(D, Hd, **bf)
+            pk.w3T = torch.empty(Hd, D, **bf)
+
+    def p(self, i: int, name: str) -> Tensor:
+        return self.layout.view(self.flat_param, f"blocks.{i}.{name}")
+
+    def g(self, i: int, name: str) -> Tensor:
+        return self.layout.view(self.flat_grad, f"blocks.{i}.{name}")
+
+    def _span(self, flat: Tensor, i: int, first: str, rows: int, cols: int) -> Tensor:
+        o = self.layout.offset[f"blocks.{i}.{first}"]
+        return flat[o:o + rows * cols].view(rows, cols)
+
+    def repack(self) -> None:
+        """f32 master -> bf16 GEMM operands (W and W^T), after every optimizer step."""
+        cfg = self.cfg
+        D, Hd = cfg.width, cfg.hidden
+        for i, pk in enumerate(self.packs):
+            last = i == cfg.layers - 1
+            if not last:
+                ops.cast_transpose(self._span(self.flat_param, i, "attn.q_proj.weight", 3 * D, D), 3 * D, D,
+                                   dst=pk.wqkv, dst_t=pk.wqkvT)
+                pk.bqkv[:D].copy_(self.p(i, "attn.q_bias"))
+                pk.bqkv[2 * D:].copy_(self.p(i, "attn.v_bias"))
+            else:
+                ops.cast_transpose(self.p(i, "attn.v_proj.weight"), D, D, dst=pk.wv, dst_t=pk.wvT)
+            ops.cast_transpose(self.p(i, "attn.proj.weight"), D, D, dst=pk.wproj, dst_t=pk.wprojT)
+            ops.cast_transpose(self._span(self.flat_param, i, "mlp.w1.weight", 2 * Hd, D), 2 * Hd, D,
+                               dst=pk.w12, dst_t=pk.w12T)
+            ops.cast_transpose(self.p(i, "mlp.w3.weight"), D, Hd, dst=pk.w3, dst_t=pk.w3T)
+
+    # ------------------------------------------------------------------ forward
+    def tape(self, B: int) -> _Tape:
+        if self._tape is None or self._tape.B != B:
+            self._tape = _Tape(self.cfg, B, self.device)
+        return self._tape
+
+    def forward(self, images: Tensor) -> Tensor:
+        """encode_dense with everything the backward needs kept on the tape.
+        Returns the NHWC map [B,g,g,C] f32 (a view of the tape)."""
+        cfg, fr = self.cfg, self.frozen
+        D, Hd, N = cfg.width, cfg.hidden, cfg.tokens
+        B = images.shape[0]
+        t = self.tape(B)
+        M = t.M
+        eps = cfg.ln_eps
+        # embed (frozen): same kernels as the teacher
+        patches = ops.im2col_patches(images, cfg.patch, fr.k_pe_pad)
+        ops.gemm(patches, fr.pe_w, t.x[0], M=B * (N - 1), N=D, K=fr.k_pe_pad, mode=L.EPI_TOKENS, bias=fr.pe_b,
+                 pos_embed=fr.pos, tokens=N)
+        ops.fill_cls_rows(fr.cls, fr.pos, t.x[0].view(B, N, D))
+        for i, pk in enumerate(self.packs):
+            last = i == cfg.layers - 1
+            st = t.stats[i]
+            x = t.x[i]
+            ops.layernorm_fwd(x, M, D, self.p(i, "norm1.weight"), self.p(i, "norm1.bias"), eps, t.u[i], mean=st[0], rstd=st[1])
+            if not last:
+                ops.gemm(t.u[i], pk.wqkv, t.qkv[i], M=M, mode=L.EPI_QKV_ROPE, bias=pk.bqkv,
+                         rope=(fr.rope_cos, fr.rope_sin), tokens=N, rope_cols=2 * D)
+                ops.attention_fwd(t.qkv[i], B, N, cfg.heads, self.scale, t.att[i], t.lse[i])
+            else:
+                ops.gemm(t.u[i], pk.wv, t.att[i], M=M, bias=self.p(i, "attn.v_bias"))
+            ops.layernorm_fwd(t.att[i], M, D, self.p(i, "attn.inner_attn_ln.weight"), self.p(i, "attn.inner_attn_ln.bias"),
+                              eps, t.aln[i], mean=st[2], rstd=st[3])
+            ops.gemm(t.aln[i], pk.wproj, t.xmid[i], M=M, bias=self.p(i, "attn.proj.bias"), residual=x)
+            ops.layernorm_fwd(t.xmid[i], M, D, self.p(i, "norm2.weight"), self.p(i, "norm2.bias"), eps, t.u2[i],
+                              mean=st[4], rstd=st[5])
+            b12 = self._span(self.flat_param, i, "mlp.w1.bias", 1, 2 * Hd).view(-1)
+            ops.gemm(t.u2[i], pk.w12, t.x12[i], M=M, bias=b12)
+            ops.swiglu_fwd(t.x12[i], M, Hd, t.h[i], split=True)
+            ops.layernorm_fwd(t.h[i], M, Hd, self.p(i, "mlp.ffn_ln.weight"), self.p(i, "mlp.ffn_ln.bias"), eps, t.hln[i],
+                              mean=st[6], rstd=st[7])
+            ops.gemm(t.hln[i], pk.w3, t.x[i + 1], M=M, bias=self.p(i, "mlp.w3.bias"), residual=t.xmid[i])
+        g = cfg.grid
+        ops.layernorm_fwd(t.x[cfg.layers], t.Mp, D, fr.norm_g, fr.norm_b, eps, t.tok_ln, row_div=g * g, row_off=1,
+                          mean=t.tok_stats[0], rstd=t.tok_stats[1])
+        ops.gemm(t.tok_ln, fr.head_w, t.head, M=t.Mp, bias=fr.head_b)
+        L.call("cs_l2norm_fwd", t.head.data_ptr(), t.Mp, cfg.embed_dim, t.dense.data_ptr(), t.inv_norm.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
+        return t.dense.view(B, g, g, cfg.embed_dim)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, d_dense: Tensor) -> None:
+        """Gradient of the dense map w.r.t. every trainable block parameter, written into
+        self.flat_grad[:n_grad] (overwritten, not accumulated: accum_freq == 1, train.py:89)."""
+        cfg, fr, t = self.cfg, self.frozen, self._tape
+        D, Hd, N, H = cfg.width, cfg.hidden, cfg.tokens, cfg.heads
+        B, M, Mp = t.B, t.M, t.Mp
+        g2 = cfg.grid * cfg.grid
+        ws = t.col_ws
+        stream = torch.cuda.current_stream().cuda_stream
+        # tail: normalise -> head -> final LN (all frozen: input gradients only)
+        L.call("cs_l2norm_bwd", t.dense.data_ptr(), t.inv_norm.data_ptr(), d_dense.data_ptr(), Mp, cfg.embed_dim,
+               t.d_head.data_ptr(), stream)
+        ops.cast_transpose(t.d_head, Mp, cfg.embed_dim, dst=t.d_head_bf)
+        d_tok = t.g_D2[:Mp]
+        ops.gemm(t.d_head_bf, self.head_wT, d_tok, M=Mp)
+        dx = t.dx
+        dx.zero_()                                                     # CLS rows get no gradient from the tail
+        ops.layernorm_bwd_dx(d_tok, t.x[cfg.layers], Mp, D, t.tok_stats[0], t.tok_stats[1], fr.norm_g, dx,
+                             row_div=g2, row_off=1, row_mapped=True)
+        for i in range(cfg.layers - 1, -1, -1):
+            pk, st = self.packs[i], t.stats[i]
+            last = i == cfg.layers - 1
+            # ---- MLP branch: x_out = xmid + w3(hln) + b3
+            ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
+            ops.col_reduce(dx, M, D, self.g(i, "mlp.w3.bias"), ws)
+            ops.cast_transpose(t.hln[i], M, Hd, dst_t=t.act_T_Hd)
+            ops.gemm(t.g_T_D, t.act_T_Hd, self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M)           # dW3 = dx^T hln
+            ops.gemm(t.g_bf_D, pk.w3T, t.g_Hd, M=M)                                               # d_hln
+            ops.col_reduce(t.g_Hd, M, Hd, self.g(i, "mlp.ffn_ln.bias"), ws, x=t.h[i], mean=st[6], rstd=st[7],
+                           dgamma=self.g(i, "mlp.ffn_ln.weight"))
+            ops.layernorm_bwd_dx(t.g_Hd, t.h[i], M, Hd, st[6], st[7], self.p(i, "mlp.ffn_ln.weight"), t.g_Hd2)  # d_h
+            ops.swiglu_bwd(t.x12[i], t.g_Hd2, M, Hd, t.g_2Hd, split=True)                         # d_x12
+            ops.cast_transpose(t.g_2Hd, M, 2 * Hd, dst_t=t.g_T_2Hd)
+            ops.cast_transpose(t.u2[i], M, D, dst_t=t.act_T_D)
+            ops.gemm(t.g_T_2Hd, t.act_T_D, self._span(self.flat_grad, i, "mlp.w1.weight", 2 * Hd, D),
+                     M=2 * Hd, N=D, K=M)                                                          # dW1|dW2
+            ops.col_reduce(t.g_2Hd, M, 2 * Hd, self._span(self.flat_grad, i, "mlp.w1.bias", 1, 2 * Hd).view(-1), ws)
+            ops.gemm(t.g_2Hd, pk.w12T, t.g_D2, M=M)                                               # d_u2
+            ops.col_reduce(t.g_D2, M, D, self.g(i, "norm2.bias"), ws, x=t.xmid[i], mean=st[4], rstd=st[5],
+                           dgamma=self.g(i, "norm2.weight"))
+            ops.layernorm_bwd_dx(t.g_D2, t.xmid[i], M, D, st[4], st[5], self.p(i, "norm2.weight"), dx, add=dx)  # d_xmid
+            # ---- attention branch: xmid = x + proj(aln) + b
+            ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
+            ops.col_reduce(dx, M, D, self.g(i, "attn.proj.bias"), ws)
+            ops.cast_transpose(t.aln[i], M, D, dst_t=t.act_T_D)
+            ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.proj.weight"), M=D, N=D, K=M)            # dWproj
+            ops.gemm(t.g_bf_D, pk.wprojT, t.g_D2, M=M)                                            # d_aln
+            ops.col_reduce(t.g_D2, M, D, self.g(i, "attn.inner_attn_ln.bias"), ws, x=t.att[i], mean=st[2], rstd=st[3],
+                           dgamma=self.g(i, "attn.inner_attn_ln.weight"))
+            d_att = t.g_bf_D
+            ops.layernorm_bwd_dx(t.g_D2, t.att[i], M, D, st[2], st[3], self.p(i, "attn.inner_attn_ln.weight"), d_att)
+            ops.cast_transpose(t.u[i], M, D, dst_t=t.act_T_D)
+            if not last:
+                ops.attention_bwd(t.qkv[i], t.att[i], d_att, t.lse[i], B, N, H, self.scale,
+                                  (fr.rope_cos, fr.rope_sin), t.delta, t.g_3D)                    # d_qkv (raw projections)
+                ops.cast_transpose(t.g_3D, M, 3 * D, dst_t=t.g_T_3D)
+                ops.gemm(t.g_T_3D, t.act_T_D, self._span(self.flat_grad, i, "attn.q_proj.weight", 3 * D, D),
+                         M=3 * D, N=D, K=M)                                                       # dWq|dWk|dWv
+                ops.col_reduce(t.g_3D, M, D, self.g(i, "attn.q_bias"), ws, lddy=3 * D)
+                ops.col_reduce(t.g_3D[:, 2 * D:], M, D, self.g(i, "attn.v_bias"), ws, lddy=3 * D)
+                ops.gemm(t.g_3D, pk.wqkvT, t.g_D2, M=M)                                           # d_u
+            else:
+                ops.cast_transpose(d_att, M, D, dst_t=t.g_T_D)
+                ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.v_proj.weight"), M=D, N=D, K=M)
+                ops.col_reduce(d_att, M, D, self.g(i, "attn.v_bias"), ws)
+                ops.gemm(d_att, pk.wvT, t.g_D2, M=M)
+            ops.col_reduce(t.g_D2, M, D, self.g(i, "norm1.bias"), ws, x=t.x[i], mean=st[0], rstd=st[1],
+                           dgamma=self.g(i, "norm1.weight"))
+            if i > 0:   # the embedding below block 0 is frozen: its input gradient is not needed
+                ops.layernorm_bwd_dx(t.g_D2, t.x[i], M, D, st[0], st[1], self.p(i, "norm1.weight"), dx, add=dx)

@@ -110,8 +110,10 @@ int cs_fill_cls_rows(const float* cls_token, const float* pos_embed, int B, int 
                      void* stream);
 
 /* LayerNorm forward (eva_clip/transformer.py:52-58, eps from model.py:123), one row per warp.
- *   x: [*, ldx] f32 or bf16;  logical row m reads physical row  m + (row_div>0 ? m/row_div+row_off : 0)
- *   (row_div = tokens-1,row_off=1 skips each image's CLS row; row_div=1,row_off... see host code);
+ *   x: [*, ldx] f32 or bf16;  logical row m reads physical row
+ *        m*row_mul + (row_div > 0 ? m/row_div : 0) + row_off
+ *   (identity: mul 1, div 0, off 0;  CLS rows only: mul = tokens;  patch rows only:
+ *    div = tokens-1, off = 1);
  *   y [M, ldy] bf16;  mean/rstd [M] f32 optional (NULL to skip; needed for backward). */
 int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, int64_t M, int D,
                      int row_div, int row_mul, int row_off,
@@ -167,6 +169,58 @@ int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, voi
 /* f32 -> bf16 cast of a [rows, cols] matrix into a (possibly wider, zero padded) bf16 matrix. */
 int cs_cast_pad_bf16(const float* src, int64_t rows, int64_t cols, int64_t lds, void* dst_bf16,
                      int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Student backward (autograd of the tower as driven by train.py:96 `backward(total_loss)`)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Softmax-attention backward for head_dim 64 (replaces the xformers / ATen backward of
+ * eva_vit_model.py:206-217).  Inputs are the tensors of cs_attention_fwd plus d_out [B*N,D] bf16;
+ * output dqkv [B*N,3D] bf16 holds dq | dk | dv.  When rope tables are given the rotation applied
+ * by the CS_EPI_QKV_ROPE epilogue is undone on dq/dk (patch tokens only), i.e. the result is the
+ * gradient w.r.t. the raw projections.  delta_ws: B*H*N floats of scratch. Deterministic. */
+int cs_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                     int B, int N, int H, float scale, const float* rope_cos, const float* rope_sin,
+                     float* delta_ws, void* dqkv_bf16, void* stream);
+
+/* src [M,N] (f32|bf16, ld lds) -> dst [M,ldd] bf16 (optional) and its transpose dst_t [N,ldt] bf16
+ * (optional): operand staging for the dgrad (dY·W) and wgrad (dY^T·X) GEMMs. */
+int cs_cast_transpose_bf16(const void* src, cs_dtype_t dtype, int64_t M, int N, int64_t lds,
+                           void* dst_bf16, int64_t ldd, void* dst_t_bf16, int64_t ldt, void* stream);
+
+/* LayerNorm backward w.r.t. the input:  dx = rstd*(g*dy - mean(g*dy) - xhat*mean(g*dy*xhat)) (+ add).
+ * x uses the forward's row map; when dx_row_mapped != 0, dx/add rows use it too (scatter back
+ * into the [B,N,D] residual gradient).  */
+int cs_layernorm_bwd_dx(const void* dy, cs_dtype_t dy_dtype, int64_t lddy, const void* x,
+                        cs_dtype_t x_dtype, int64_t ldx, int64_t M, int D, int row_div, int row_mul,
+                        int row_off, const float* mean, const float* rstd, const float* gamma,
+                        const float* add, int64_t ldadd, void* dx, cs_dtype_t dx_dtype, int64_t lddx,
+                        int dx_row_mapped, void* stream);
+
+/* Column reductions over the M rows, deterministic two-stage:
+ *   dbeta[c]  = sum_m dy[m,c]                       (bias gradients when x == NULL)
+ *   dgamma[c] = sum_m dy[m,c] * (x[m,c]-mean[m])*rstd[m]   (LayerNorm weight gradient, x != NULL)
+ * workspace: at least 128*2*D floats. */
+int cs_col_reduce(const void* dy, cs_dtype_t dy_dtype, int64_t lddy, const void* x, cs_dtype_t x_dtype,
+                  int64_t ldx, int64_t M, int D, int row_div, int row_mul, int row_off,
+                  const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                  float* workspace, int64_t workspace_floats, void* stream);
+
+/* SwiGLU (eva_vit_model.py:98-101) on pre-activations x12 [M, 2*Hd] bf16:
+ *   split_layout != 0: gate = x12[:, j], up = x12[:, Hd + j]           (weights [w1; w2] stacked)
+ *   split_layout == 0: the packed layout of cs_pack_swiglu_weights (gate|up interleaved by 128)
+ *   h = silu(gate) * up  and its backward (dx12 in the same layout as x12). */
+int cs_swiglu_fwd(const void* x12_bf16, int64_t M, int Hd, int64_t ld12, void* h_bf16, int64_t ldh,
+                  int split_layout, void* stream);
+int cs_swiglu_bwd(const void* x12_bf16, const void* dh_bf16, int64_t M, int Hd, int64_t ld12,
+                  int64_t lddh, void* dx12_bf16, int split_layout, void* stream);
+
+/* Fused AdamW over a flat f32 buffer — torch.optim.AdamW semantics as configured at
+ * main.py:205-213 (decoupled weight decay, bias correction); grad is multiplied by grad_scale
+ * first (1/world_size after a sum all-reduce). `step` is 1-based. */
+int cs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int step,
+                  double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
