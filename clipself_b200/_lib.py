@@ -20,8 +20,8 @@ vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 class GemmEpilogue(C.Structure):
     """cs_gemm_epilogue_t"""
     _fields_ = [("mode", C.c_int32), ("out_dtype", C.c_int32), ("out", vp), ("ldo", i64),
-                ("bias", vp), ("residual", vp), ("ldr", i64), ("rope_cos", vp), ("rope_sin", vp),
-                ("tokens", C.c_int32), ("rope_cols", C.c_int32), ("pos_embed", vp),
+                ("bias", vp), ("residual", vp), ("ldr", i64), ("rope_pos", vp), ("rope_freq", vp),
+                ("rope_grid", C.c_int32), ("tokens", C.c_int32), ("rope_cols", C.c_int32), ("pos_embed", vp),
                 ("alpha", f32), ("reserved", C.c_int32)]
 
 
@@ -85,8 +85,16 @@ def check(rc: int, what: str) -> None:
         raise ClipselfB200Error(f"{what} failed (code {rc}): {lib().cs_last_error().decode()}")
 
 
+# kernels launched by one successful call of each entry point (for bench.py's `gpu_launches`)
+KERNELS_PER_CALL = {"cs_roi_align_fwd": 2, "cs_cosine_loss_fwd": 2, "cs_col_reduce": 2, "cs_attention_bwd": 3,
+                    "cs_abi_version": 0, "cs_device_info": 0}
+launch_count = 0
+
+
 def call(name: str, *args) -> None:
+    global launch_count
     check(getattr(lib(), name)(*args), name)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
 def require_device() -> dict:

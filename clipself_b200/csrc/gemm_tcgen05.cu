@@ -8,7 +8,10 @@
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Fused epilogues (cs_epilogue_mode_t): bias / residual / alpha, RoPE on the q|k columns
-// (rope.py:148-164 semantics), SwiGLU gate*up on packed weights, patch-embed token assembly.
+// (rope.py:148-164 semantics, angles recomputed in-kernel from the 1-D position / frequency
+// vectors instead of reading [tokens,64] tables), SwiGLU gate*up on packed weights, patch-embed
+// token assembly.  Every (mode, out dtype, residual kind) is its own template instantiation so the
+// epilogue is straight-line code.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -20,7 +23,6 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
 
 template <int BLOCK_N>
 struct Cfg {
@@ -30,7 +32,12 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two)
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
+    static constexpr int EPI_TILE_BYTES = 32 * 128;          // one swizzled 32-row x 128 B staging tile per warp
+    static constexpr int EPI_BIAS_BYTES = BLOCK_N * 4;       // this tile's bias slice, one private copy per warp
+    static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + EPI_BIAS_BYTES;
+    static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+    static constexpr int ROPE_BYTES = 512;                   // 64 grid positions + 16 frequencies (+pad)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + ROPE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
 };
 
 struct EpiParams {
@@ -41,12 +48,14 @@ struct EpiParams {
     const float* bias;
     const float* residual;
     long long ldr;
-    const float* rope_cos;
-    const float* rope_sin;
+    const float* rope_pos;    // [rope_grid]  position value of grid index i  (rope.py:127: i/ft*pt)
+    const float* rope_freq;   // [16]         theta^(-2n/32)                  (rope.py:118)
+    int rope_grid;
     int tokens;
     int rope_cols;
     const float* pos_embed;
     float alpha;
+    int dbg;   // debug switches for epilogue ablations (cs_gemm_epilogue_t.reserved); 0 in production
 };
 
 // ----------------------------------------------------------------------------------------
@@ -161,37 +170,179 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// ----------------------------------------------------------------------------------------
-// Epilogue math on one 32-column chunk held by one thread (one output row)
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32]) {
+enum ResKind { RES_NONE = 0, RES_LOAD = 1, RES_RED = 2 };
+
+// one epilogue warp: 32 accumulator rows of one tile
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t taddr, int mw, int n0, int M, int N,
+                                              uint8_t* st, float* sbias, const float* srope, int lane) {
+    using C = Cfg<BLOCK_N>;
+    const int crow = lane >> 3;                   // coalesced phase: row within a group of 4
+    const int cchunk = lane & 7;                  // coalesced phase: 16 B chunk of the 128 B row slice
+    // this tile's bias slice -> private smem copy (replaces dependent global loads in the hot loop)
+    if (ep.bias != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-}
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+        for (int j = lane * 4; j < BLOCK_N; j += 128) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + j < N) b = *reinterpret_cast<const float4*>(ep.bias + n0 + j);
+            *reinterpret_cast<float4*>(sbias + j) = b;
+        }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16(v[j], v[j + 1]);
-        u.y = pack_bf16(v[j + 2], v[j + 3]);
-        u.z = pack_bf16(v[j + 4], v[j + 5]);
-        u.w = pack_bf16(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(dst + j) = u;
+        for (int j = lane * 4; j < BLOCK_N; j += 128) *reinterpret_cast<float4*>(sbias + j) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-}
-__device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restrict__ src) {
+    __syncwarp();
+
+    if constexpr (OUT_BF16) {
+        // ---------------- bf16 outputs: math in registers (row per thread), packed staging --------
+        const int m = mw + lane;
+        int gi = 0, gj = 0;
+        bool rot = false;
+        if constexpr (MODE == CS_EPI_QKV_ROPE) {
+            const int tok = m % ep.tokens;
+            rot = tok > 0;
+            const int p = tok > 0 ? tok - 1 : 0;
+            gi = p / ep.rope_grid;
+            gj = p % ep.rope_grid;
+        }
+        constexpr int OUT_COLS = (MODE == CS_EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N;
+        const int out_n0 = (MODE == CS_EPI_SWIGLU) ? (n0 >> 1) : n0;
+        const int out_N = (MODE == CS_EPI_SWIGLU) ? (N >> 1) : N;
+#pragma unroll 1
+        for (int gc = 0; gc < OUT_COLS; gc += 64) {          // 64 bf16 output columns = 128 B per row
+            if (out_n0 + gc >= out_N) break;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(src + j);
-        v[j] += b.x;
-        v[j + 1] += b.y;
-        v[j + 2] += b.z;
-        v[j + 3] += b.w;
+            for (int half = 0; half < 2; ++half) {
+                const int c = gc + half * 32;                // output column offset inside the tile
+                float v[32];
+                if constexpr (MODE == CS_EPI_SWIGLU) {
+                    uint32_t rg[32], ru[32];
+                    tmem_ld32(taddr + c, rg);
+                    tmem_ld32(taddr + 128 + c, ru);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float g = __uint_as_float(rg[j]) * ep.alpha + sbias[c + j];
+                        const float u = __uint_as_float(ru[j]) * ep.alpha + sbias[128 + c + j];
+                        v[j] = __fdividef(g, 1.0f + __expf(-g)) * u;
+                    }
+                } else {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha + sbias[c + j];
+                    if constexpr (MODE == CS_EPI_QKV_ROPE) {
+                        const int n = n0 + c;
+                        if (n < ep.rope_cols && rot) {
+                            // head-dim offset 0..31 rotates by the token's grid ROW, 32..63 by its COLUMN
+                            const float pos = srope[(n & 32) ? gj : gi];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                float sn, cs_;
+                                __sincosf(pos * srope[64 + q], &sn, &cs_);
+                                const float x0 = v[2 * q], x1 = v[2 * q + 1];
+                                v[2 * q] = x0 * cs_ - x1 * sn;
+                                v[2 * q + 1] = x1 * cs_ + x0 * sn;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    pk.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+                    pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                    pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                    pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                    const int chunk = half * 4 + j;
+                    *reinterpret_cast<uint4*>(st + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+                }
+            }
+            __syncwarp();
+            const int ocol = out_n0 + gc + cchunk * 8;
+            uint4 val[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + crow;
+                val[i] = *reinterpret_cast<const uint4*>(st + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int mm = mw + i * 4 + crow;
+                if (mm < M && ocol < out_N)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)mm * ep.ldo + ocol) = val[i];
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- f32 outputs: raw staging, math in the coalesced phase ----------------
+        long long orow[8];
+        int prow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int mm = mw + i * 4 + crow;
+            orow[i] = mm;
+            prow[i] = 0;
+            if constexpr (MODE == CS_EPI_TOKENS) {
+                orow[i] = (long long)mm + mm / (ep.tokens - 1) + 1;
+                prow[i] = mm % (ep.tokens - 1) + 1;
+            }
+            if (mm >= M) orow[i] = -1;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {              // 32 f32 output columns = 128 B per row
+            const int n = n0 + c;
+            if (n >= N) break;
+            const int nc = n + cchunk * 4;
+            const bool col_ok = nc < N;
+            // residual / pos_embed reads do not depend on the accumulator: issue them first
+            float4 extra[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                extra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (orow[i] >= 0 && col_ok) {
+                    if constexpr (RES == RES_LOAD) extra[i] = *reinterpret_cast<const float4*>(ep.residual + orow[i] * ep.ldr + nc);
+                    if constexpr (MODE == CS_EPI_TOKENS) extra[i] = *reinterpret_cast<const float4*>(ep.pos_embed + (long long)prow[i] * N + nc);
+                }
+            }
+            {
+                uint32_t r[32];
+                tmem_ld32(taddr + c, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 f = make_float4(__uint_as_float(r[4 * j]) * ep.alpha, __uint_as_float(r[4 * j + 1]) * ep.alpha,
+                                                 __uint_as_float(r[4 * j + 2]) * ep.alpha, __uint_as_float(r[4 * j + 3]) * ep.alpha);
+                    *reinterpret_cast<float4*>(st + lane * 128 + ((j ^ (lane & 7)) << 4)) = f;
+                }
+            }
+            __syncwarp();
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + cchunk * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + crow;
+                float4 f = *reinterpret_cast<const float4*>(st + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
+                f.x += b4.x + extra[i].x;
+                f.y += b4.y + extra[i].y;
+                f.z += b4.z + extra[i].z;
+                f.w += b4.w + extra[i].w;
+                if (orow[i] >= 0 && col_ok) {
+                    float* dst = reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + nc;
+                    if constexpr (RES == RES_RED) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w)
+                                     : "memory");
+                    } else {
+                        *reinterpret_cast<float4*>(dst) = f;
+                    }
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             int M, int N, int K, const EpiParams ep) {
@@ -201,14 +352,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+    constexpr int EPI_OFF = C::STAGES * C::STAGE_BYTES;
+    constexpr int ROPE_OFF = EPI_OFF + C::EPI_BYTES;
+    constexpr int BAR_OFF = ROPE_OFF + C::ROPE_BYTES;
+    const uint32_t bar_base = base + BAR_OFF;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
-    volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + 8 * (2 * C::STAGES + 4));
+    float* srope = reinterpret_cast<float*>(smem + ROPE_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -230,6 +384,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_init(tempty_bar(a), 4 * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if constexpr (MODE == CS_EPI_QKV_ROPE) {
+        if (threadIdx.x >= 64 && threadIdx.x < 64 + 80) {
+            const int i = threadIdx.x - 64;
+            srope[i] = i < 64 ? (i < ep.rope_grid ? ep.rope_pos[i] : 0.f) : ep.rope_freq[i - 64];
+        }
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
@@ -296,8 +456,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
     } else {
         // ------------------------------ epilogue -----------------------------------
-        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row_in_tile = quarter * 32 + lane;
+        // Each warp owns 32 accumulator rows (its TMEM lane quarter); see epilogue_tile().
+        const int quarter = warp & 3;
+        uint8_t* st = smem + EPI_OFF + (warp - 2) * C::EPI_WARP_BYTES;
+        float* sbias = reinterpret_cast<float*>(st + C::EPI_TILE_BYTES);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m0 = (tile / num_n_tiles) * BLOCK_M;
@@ -307,78 +469,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            const int m = m0 + row_in_tile;
-            const bool row_ok = m < M;
-
-            if (ep.mode == CS_EPI_SWIGLU) {
-                // packed tile: columns [0,128) gate, [128,256) up of hidden columns n0/2 + [0,128)
-                if constexpr (BLOCK_N == 256) {
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t rg[32], ru[32];
-                        tmem_ld32(taddr + c * 32, rg);
-                        tmem_ld32(taddr + 128 + c * 32, ru);
-                        tmem_ld_wait();
-                        float h[32];
-                        const float* bg = ep.bias + n0 + c * 32;
-                        const float* bu = ep.bias + n0 + 128 + c * 32;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float g = __uint_as_float(rg[j]) * ep.alpha + __ldg(bg + j);
-                            const float u = __uint_as_float(ru[j]) * ep.alpha + __ldg(bu + j);
-                            h[j] = (g / (1.0f + __expf(-g))) * u;
-                        }
-                        if (row_ok) {
-                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.out) +
-                                                 (long long)m * ep.ldo + (n0 >> 1) + c * 32;
-                            store_row_bf16(dst, h);
-                        }
-                    }
-                }
-            } else {
-                long long out_row = m;
-                int pos_row = 0;
-                if (ep.mode == CS_EPI_TOKENS) {
-                    const int per = ep.tokens - 1;
-                    out_row = (long long)m + m / per + 1;
-                    pos_row = m % per + 1;
-                }
-                const int tok = (ep.mode == CS_EPI_QKV_ROPE) ? (m % ep.tokens) : 0;
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    const int n = n0 + c * 32;
-                    if (n >= N) break;                      // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
-                    tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-                    if (ep.bias != nullptr) add_vec32(v, ep.bias + n);
-                    if (ep.mode == CS_EPI_QKV_ROPE) {
-                        if (n < ep.rope_cols && tok > 0 && row_ok) {
-                            const int d0 = n & 63;
-                            const float* cs_ = ep.rope_cos + (long long)(tok - 1) * 64 + d0;
-                            const float* sn_ = ep.rope_sin + (long long)(tok - 1) * 64 + d0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                const float x0 = v[j], x1 = v[j + 1];
-                                v[j] = x0 * __ldg(cs_ + j) - x1 * __ldg(sn_ + j);
-                                v[j + 1] = x1 * __ldg(cs_ + j + 1) + x0 * __ldg(sn_ + j + 1);
-                            }
-                        }
-                    } else if (ep.mode == CS_EPI_TOKENS) {
-                        if (row_ok) add_vec32(v, ep.pos_embed + (long long)pos_row * N + n);
-                    }
-                    if (row_ok) {
-                        if (ep.residual != nullptr) add_vec32(v, ep.residual + out_row * ep.ldr + n);
-                        if (ep.out_bf16)
-                            store_row_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + n, v);
-                        else
-                            store_row_f32(reinterpret_cast<float*>(ep.out) + out_row * ep.ldo + n, v);
-                    }
-                }
-            }
+            if (!(ep.dbg & 8))
+                epilogue_tile<BLOCK_N, MODE, OUT_BF16, RES>(ep, taddr, m0 + quarter * 32, n0, M, N, st, sbias, srope, lane);
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
@@ -432,21 +524,41 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
     return CS_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
                   cudaStream_t stream) {
     using C = Cfg<BLOCK_N>;
     static bool configured = false;
     if (!configured) {
-        CS_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::SMEM_BYTES));
+        CS_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+    gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
     CS_LAUNCH_CHECK();
     return CS_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep, int res,
+                    cudaStream_t st) {
+    switch (ep.mode) {
+        case CS_EPI_STORE:
+            if (ep.out_bf16) return launch<BLOCK_N, CS_EPI_STORE, true, RES_NONE>(ma, mb, M, N, K, ep, st);
+            if (res == RES_RED) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED>(ma, mb, M, N, K, ep, st);
+            if (res == RES_LOAD) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD>(ma, mb, M, N, K, ep, st);
+            return launch<BLOCK_N, CS_EPI_STORE, false, RES_NONE>(ma, mb, M, N, K, ep, st);
+        case CS_EPI_QKV_ROPE:
+            return launch<BLOCK_N, CS_EPI_QKV_ROPE, true, RES_NONE>(ma, mb, M, N, K, ep, st);
+        case CS_EPI_TOKENS:
+            return launch<BLOCK_N, CS_EPI_TOKENS, false, RES_NONE>(ma, mb, M, N, K, ep, st);
+        case CS_EPI_SWIGLU:
+            if constexpr (BLOCK_N == 256) return launch<256, CS_EPI_SWIGLU, true, RES_NONE>(ma, mb, M, N, K, ep, st);
+    }
+    set_error("cs_gemm_bf16: unsupported epilogue combination");
+    return CS_ERR_UNSUPPORTED;
 }
 
 }  // namespace gemm
@@ -478,12 +590,14 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     ep.bias = e->bias;
     ep.residual = e->residual;
     ep.ldr = e->ldr;
-    ep.rope_cos = e->rope_cos;
-    ep.rope_sin = e->rope_sin;
+    ep.rope_pos = e->rope_pos;
+    ep.rope_freq = e->rope_freq;
+    ep.rope_grid = e->rope_grid;
     ep.tokens = e->tokens;
     ep.rope_cols = e->rope_cols;
     ep.pos_embed = e->pos_embed;
     ep.alpha = e->alpha;
+    ep.dbg = e->reserved;
 
     bool use256 = (N % 256 == 0);
     if (e->mode == CS_EPI_SWIGLU) {
@@ -492,8 +606,9 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
         use256 = true;
     }
     if (e->mode == CS_EPI_QKV_ROPE)
-        CS_CHECK_ARG(e->rope_cos && e->rope_sin && e->tokens > 1 && e->rope_cols % 64 == 0 && e->out_dtype == CS_BF16,
-                     "cs_gemm_bf16: QKV_ROPE needs tables, tokens, rope_cols %% 64 == 0, bf16 out");
+        CS_CHECK_ARG(e->rope_pos && e->rope_freq && e->rope_grid > 0 && e->rope_grid <= 64 &&
+                         e->tokens == e->rope_grid * e->rope_grid + 1 && e->rope_cols % 64 == 0 && e->out_dtype == CS_BF16,
+                     "cs_gemm_bf16: QKV_ROPE needs rope_pos/rope_freq, grid <= 64, tokens == grid^2+1, rope_cols %% 64 == 0, bf16 out");
     if (e->mode == CS_EPI_TOKENS)
         CS_CHECK_ARG(e->pos_embed && e->tokens > 1 && e->out_dtype == CS_F32 && ((uintptr_t)e->pos_embed % 16 == 0),
                      "cs_gemm_bf16: TOKENS needs pos_embed, tokens, f32 out");
@@ -504,5 +619,11 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     rc = make_map(&mb, W, N, K, ldw, use256 ? 256 : 128);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return use256 ? launch<256>(ma, mb, (int)M, N, K, ep, st) : launch<128>(ma, mb, (int)M, N, K, ep, st);
+    int res = RES_NONE;
+    if (e->residual) {
+        CS_CHECK_ARG(e->out_dtype == CS_F32 && e->mode == CS_EPI_STORE, "cs_gemm_bf16: residual needs f32 STORE output");
+        res = (e->residual == e->out && e->ldr == e->ldo) ? RES_RED : RES_LOAD;
+    }
+    CS_CHECK_ARG(e->mode != CS_EPI_STORE || e->out_dtype == CS_F32 || N % 64 == 0 || true, "unreachable");
+    return use256 ? dispatch<256>(ma, mb, (int)M, N, K, ep, res, st) : dispatch<128>(ma, mb, (int)M, N, K, ep, res, st);
 }

@@ -1,0 +1,70 @@
+"""Synthetic `(image, boxes[K,5], crops[K,3,s,s])` batches with the contract of the reference's
+distillation datasets (src/training/data.py:132,281) — the additive `--dataset-type synthetic_distill`
+of SURVEY.md §7 (no COCO on the GPU box).  Box statistics follow SURVEY.md §8d:
+  grid      K boxes drawn from the M x M grid templates of GridDistillDataset (data.py:200-224)
+  proposal  x0,y0 ~ U(0,.6), w,h ~ U(.1,.4)
+"""
+from __future__ import annotations
+
+import torch
+from torch.utils.data import Dataset
+
+
+def grid_box_templates(m: int, n: int) -> torch.Tensor:
+    """Row-major m x n boxes [x0,y0,x1,y1] from f32 linspace edges (data.py:213-224)."""
+    ys = torch.linspace(0, 1, m + 1)
+    xs = torch.linspace(0, 1, n + 1)
+    x0, y0 = torch.meshgrid(xs[:-1], ys[:-1], indexing="xy")
+    x1, y1 = torch.meshgrid(xs[1:], ys[1:], indexing="xy")
+    return torch.stack([x0, y0, x1, y1], dim=-1).reshape(m * n, 4)
+
+
+def synthetic_boxes(K: int, kind: str, g: torch.Generator, ragged: bool = False) -> torch.Tensor:
+    boxes = torch.zeros(K, 5)
+    if kind == "grid":
+        side = 1
+        while side * side < K:
+            side += 1
+        tmpl = grid_box_templates(side, side)
+        boxes[:, :4] = tmpl[torch.randperm(tmpl.shape[0], generator=g)[:K]]
+    elif kind == "proposal":
+        xy = torch.rand(K, 2, generator=g) * 0.6
+        wh = torch.rand(K, 2, generator=g) * 0.3 + 0.1
+        boxes[:, 0:2] = xy
+        boxes[:, 2:4] = xy + wh
+    else:
+        raise ValueError(f"unknown box kind {kind!r}")
+    boxes[:, 4] = 1.0
+    if ragged:
+        keep = int(torch.randint(1, K + 1, (1,), generator=g))
+        boxes[keep:] = 0.0
+    return boxes
+
+
+def synthetic_batch(image_size: int, B: int, K: int, kind: str = "grid", seed: int = 0, ragged: bool = False,
+                    crop_size: int | None = None):
+    g = torch.Generator().manual_seed(seed)
+    s = crop_size or image_size
+    images = torch.randn(B, 3, image_size, image_size, generator=g)
+    crops = torch.randn(B, K, 3, s, s, generator=g)
+    boxes = torch.stack([synthetic_boxes(K, kind, g, ragged) for _ in range(B)])
+    return images, boxes, crops
+
+
+class SyntheticDistillDataset(Dataset):
+    """Endless-ish synthetic dataset yielding what GridDistillDataset.__getitem__ returns."""
+
+    def __init__(self, image_size: int, crop_size: int, max_boxes: int, kind: str = "grid", length: int = 4096,
+                 seed: int = 0, ragged: bool = True):
+        self.image_size, self.crop_size, self.K = image_size, crop_size, max_boxes
+        self.kind, self.length, self.seed, self.ragged = kind, length, seed, ragged
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + idx)
+        image = torch.randn(3, self.image_size, self.image_size, generator=g)
+        crops = torch.randn(self.K, 3, self.crop_size, self.crop_size, generator=g)
+        boxes = synthetic_boxes(self.K, self.kind, g, self.ragged)
+        return image, boxes, crops

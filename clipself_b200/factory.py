@@ -1,0 +1,103 @@
+"""`open_clip.create_model` / `create_model_and_transforms` for the EVA02-CLIP models the reference's
+scripts use (src/open_clip/factory.py:111-249 with the 'eva' dispatch :145-149 into
+src/open_clip/eva_clip/factory.py:211-355).  Same arguments, same error behaviour for the cases on
+the CLIPSelf path; arguments that only concern other backbones are accepted and ignored."""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Optional, Union
+
+import torch
+
+from .configs import get_model_config, list_models  # noqa: F401  (re-export)
+from .model import CustomCLIP
+
+
+def get_cast_dtype(precision: str):
+    """eva_clip/model.py:83-89."""
+    return {"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision)
+
+
+def load_state_dict(checkpoint_path: str, map_location="cpu", model_key="model|module|state_dict", is_openai=False,
+                    skip_list=()):
+    """eva_clip/factory.py:80-106: unwrap, strip 'module.', drop rope buffers (always regenerated)."""
+    checkpoint = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+    for mk in model_key.split("|"):
+        if isinstance(checkpoint, dict) and mk in checkpoint:
+            state_dict = checkpoint[mk]
+            break
+    else:
+        state_dict = checkpoint
+    if next(iter(state_dict.items()))[0].startswith("module"):
+        state_dict = {k[7:]: v for k, v in state_dict.items()}
+    for k in list(state_dict.keys()):
+        if k in skip_list or "freqs_cos" in k or "freqs_sin" in k:
+            del state_dict[k]
+    return state_dict
+
+
+def load_checkpoint(model, checkpoint_path, model_key="model|module|state_dict", strict=False):
+    state_dict = load_state_dict(checkpoint_path, model_key=model_key)
+    pe = state_dict.get("visual.pos_embed")
+    if pe is not None and pe.shape != model.visual.pos_embed.shape:
+        raise NotImplementedError("positional-embedding resize at load time (eva_clip/utils.py:78-106) is part of the "
+                                  "variable-resolution row, SURVEY.md §8f rank 4")
+    # text tower keys are kept out of the module (not on the path) but must not make the load fail
+    incompatible = model.load_state_dict({k: v for k, v in state_dict.items() if not k.startswith("text.")},
+                                         strict=False)
+    logging.info(f"incompatible_keys.missing_keys: {incompatible.missing_keys}")
+    return incompatible
+
+
+def create_model(
+        model_name: str,
+        pretrained: Optional[str] = None,
+        precision: str = "fp32",
+        device: Union[str, torch.device] = "cpu",
+        jit: bool = False,
+        force_quick_gelu: bool = False,
+        force_custom_text: bool = False,
+        force_patch_dropout: Optional[float] = None,
+        force_image_size=None,
+        pretrained_image: bool = False,
+        pretrained_hf: bool = True,
+        cache_dir: Optional[str] = None,
+        output_dict: Optional[bool] = None,
+        require_pretrained: bool = False,
+):
+    if jit:
+        raise NotImplementedError("jit=True is an OpenAI-checkpoint path, not used by CLIPSelf")
+    cfg = get_model_config(model_name)                      # RuntimeError for unknown names, like the reference
+    if force_image_size is not None:
+        raise NotImplementedError("force_image_size needs the variable-resolution tower (SURVEY.md §8f rank 4)")
+    if precision in ("bf16", "fp16", "pure_bf16", "pure_fp16"):
+        # the reference's pure-bf16 mode dies at torchvision RoIAlign; the runnable
+        # bf16 mode is amp_bf16 = f32 master weights + bf16 tensor-core operands, which is what we run.
+        raise NotImplementedError(f"precision={precision!r}: use 'amp_bf16' (f32 master weights, bf16 tensor cores)")
+    model = CustomCLIP(embed_dim=cfg["embed_dim"], vision_cfg=cfg["vision_cfg"], text_cfg=cfg["text_cfg"])
+    if pretrained and pretrained != "eva":
+        raise RuntimeError(f"Pretrained weights ({pretrained}) not found for model {model_name}.")
+    if cache_dir:                                           # the scripts pass the checkpoint path here
+        if not os.path.exists(cache_dir):
+            raise RuntimeError(f"Pretrained weights ({cache_dir}) not found for model {model_name}.")
+        load_checkpoint(model, cache_dir)
+    elif require_pretrained:
+        raise RuntimeError(f"Pretrained weights were required for (model: {model_name}) but not loaded.")
+    model.to(device=torch.device(device))
+    model.output_dict = bool(output_dict)
+    return model
+
+
+def create_model_and_transforms(model_name: str, pretrained: Optional[str] = None, precision: str = "fp32",
+                                device="cpu", jit=False, force_quick_gelu=False, force_custom_text=False,
+                                force_patch_dropout=None, force_image_size=None, pretrained_image=False,
+                                pretrained_hf=True, image_mean=None, image_std=None, aug_cfg=None,
+                                cache_dir: Optional[str] = None, output_dict=None, det_image_size=1024,
+                                dataset_type=None):
+    """open_clip/factory.py:267-350.  The image transforms belong to the CPU data pipeline, which is
+    out of scope; the synthetic dataset does not need them, so None is returned in
+    their place."""
+    model = create_model(model_name, pretrained, precision, device, jit, force_quick_gelu, force_custom_text,
+                         force_patch_dropout, force_image_size, pretrained_image, pretrained_hf, cache_dir, output_dict)
+    return model, None, [None, None]

@@ -12,6 +12,10 @@ from ._lib import call
 Tensor = torch.Tensor
 
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream
+GEMM_PROFILE = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -153,7 +157,7 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optio
          K: Optional[int] = None, mode: int = L.EPI_STORE, bias: Optional[Tensor] = None,
          residual: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, Tensor]] = None, tokens: int = 0,
          rope_cols: int = 0, pos_embed: Optional[Tensor] = None, alpha: float = 1.0,
-         ldo: Optional[int] = None) -> Tensor:
+         ldo: Optional[int] = None, dbg: int = 0) -> Tensor:
     """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16 row-major (lda/ldw = last dim)."""
     _chk(a, torch.bfloat16, "a")
     _chk(w, torch.bfloat16, "w")
@@ -168,13 +172,22 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optio
     e.bias = _p(bias)
     e.residual = _p(residual)
     e.ldr = residual.shape[-1] if residual is not None else 0
-    e.rope_cos = _p(rope[0]) if rope is not None else None
-    e.rope_sin = _p(rope[1]) if rope is not None else None
+    e.rope_pos = _p(rope[0]) if rope is not None else None      # rope = (pos [grid], freq [16])
+    e.rope_freq = _p(rope[1]) if rope is not None else None
+    e.rope_grid = rope[0].numel() if rope is not None else 0
     e.tokens = tokens
     e.rope_cols = rope_cols
     e.pos_embed = _p(pos_embed)
     e.alpha = alpha
+    e.reserved = dbg
+    if GEMM_PROFILE is None:
+        call("cs_gemm_bf16", _p(a), a.shape[-1], _p(w), w.shape[-1], M, N, K, C.byref(e), _stream())
+        return out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     call("cs_gemm_bf16", _p(a), a.shape[-1], _p(w), w.shape[-1], M, N, K, C.byref(e), _stream())
+    e1.record()
+    GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
     return out
 
 

@@ -11,7 +11,7 @@ Reference semantics being reproduced (wusize/CLIPSelf @ 1c7fe9c):
 
 Memory layout (HBM, all f32, one allocation each for params / grads / Adam moments):
   [ 2-D weights of every block, in GEMM-friendly groups | 1-D vectors | grad-less tail ]
-   \__ weight-decay group (main.py:199-213) _________/ \_ no-decay _/ \_ never updated _/
+   '--- weight-decay group (main.py:199-213) ---------'  '- no-decay -'  '- never updated -'
   q|k|v weights of a block are adjacent ([3D,D] view = fused QKV operand and its wgrad output),
   w1|w2 likewise ([2Hd,D]).  The wgrad GEMMs and bias/LN column reductions write straight into
   the flat gradient buffer: no per-tensor copies, one all-reduce, two AdamW launches.
@@ -183,9 +183,11 @@ class StudentEngine:
         cfg, dev = self.cfg, self.device
         f = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
         fr = self.frozen
-        from .tower import rope_tables
+        from .tower import rope_tables, rope_vectors
         cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
         fr.rope_cos, fr.rope_sin = cos.to(dev), sin.to(dev)
+        pos, freq = rope_vectors(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
+        fr.rope_pos, fr.rope_freq = pos.to(dev), freq.to(dev)
         fr.k_pe = 3 * cfg.patch * cfg.patch
         fr.k_pe_pad = _round_up(fr.k_pe, 8)
         D = cfg.width
@@ -277,7 +279,7 @@ class StudentEngine:
             ops.layernorm_fwd(x, M, D, self.p(i, "norm1.weight"), self.p(i, "norm1.bias"), eps, t.u[i], mean=st[0], rstd=st[1])
             if not last:
                 ops.gemm(t.u[i], pk.wqkv, t.qkv[i], M=M, mode=L.EPI_QKV_ROPE, bias=pk.bqkv,
-                         rope=(fr.rope_cos, fr.rope_sin), tokens=N, rope_cols=2 * D)
+                         rope=(fr.rope_pos, fr.rope_freq), tokens=N, rope_cols=2 * D)
                 ops.attention_fwd(t.qkv[i], B, N, cfg.heads, self.scale, t.att[i], t.lse[i])
             else:
                 ops.gemm(t.u[i], pk.wv, t.att[i], M=M, bias=self.p(i, "attn.v_bias"))

@@ -69,6 +69,15 @@ def rope_tables(grid: int, head_dim: int, pt_seq_len: int, theta: float = 10000.
     return full.cos().reshape(-1, 2 * dim).contiguous(), full.sin().reshape(-1, 2 * dim).contiguous()
 
 
+def rope_vectors(grid: int, head_dim: int, pt_seq_len: int, theta: float = 10000.0):
+    """The two 1-D factors of the tables above: pos [grid] (rope.py:127) and freq [head_dim/4]
+    (rope.py:118), same torch ops -> angle(token, d) = pos[row or col] * freq[(d % 32) // 2]."""
+    dim = head_dim // 2
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    t = torch.arange(grid) / grid * pt_seq_len
+    return t.float().contiguous(), freqs.contiguous()
+
+
 class PackedBlock:
     __slots__ = ("wqkv", "bqkv", "wv", "bv", "wproj", "bproj", "w12", "b12", "w3", "b3",
                  "g1", "b1", "gi", "bi", "g2", "b2", "gf", "bf")
@@ -87,6 +96,8 @@ class PackedTower:
         cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
         self.rope_cos = cos.to(device)
         self.rope_sin = sin.to(device)
+        pos, freq = rope_vectors(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
+        self.rope_pos, self.rope_freq = pos.to(device), freq.to(device)
         self.k_pe = 3 * cfg.patch * cfg.patch
         self.k_pe_pad = _round_up(self.k_pe, 8)
         self.blocks: List[PackedBlock] = [PackedBlock() for _ in range(cfg.layers)]
@@ -177,7 +188,7 @@ class TowerEngine:
         x, u = ws.x, ws.u
         ops.layernorm_fwd(x, M, D, pb.g1, pb.b1, cfg.ln_eps, u)
         if with_attention:
-            ops.gemm(u, pb.wqkv, ws.qkv, M=M, mode=L.EPI_QKV_ROPE, bias=pb.bqkv, rope=(self.w.rope_cos, self.w.rope_sin),
+            ops.gemm(u, pb.wqkv, ws.qkv, M=M, mode=L.EPI_QKV_ROPE, bias=pb.bqkv, rope=(self.w.rope_pos, self.w.rope_freq),
                      tokens=N, rope_cols=2 * D)
             ops.attention_fwd(ws.qkv, B, N, cfg.heads, self.scale, ws.att)
         else:

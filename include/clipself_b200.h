@@ -136,13 +136,14 @@ typedef struct {
     const float* bias;       /* [N] or NULL */
     const float* residual;   /* [M, ldr] f32 or NULL; may alias out (in-place x += ...) */
     int64_t ldr;
-    const float* rope_cos;   /* [tokens-1, 64] f32 */
-    const float* rope_sin;
+    const float* rope_pos;   /* [rope_grid] f32: position of grid index i, i/ft*pt (rope.py:127) */
+    const float* rope_freq;  /* [16] f32: theta^(-2n/32) (rope.py:118); angle(token,d) = pos * freq   */
+    int32_t rope_grid;       /* grid side; tokens == rope_grid^2 + 1 */
     int32_t tokens;          /* tokens per image incl. CLS (QKV_ROPE, TOKENS) */
     int32_t rope_cols;       /* columns [0, rope_cols) are rotated (= 2*D for q|k|v) */
     const float* pos_embed;  /* [tokens, N] f32 (TOKENS) */
     float alpha;             /* scale applied to acc before everything else (1.0 default) */
-    int32_t reserved;
+    int32_t reserved;        /* must be 0 (debug ablation switches) */
 } cs_gemm_epilogue_t;
 
 /* C[M,N] = A[M,K] · W[N,K]^T on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM ->

@@ -82,7 +82,7 @@ def test_gemm_bf16_out_alpha(dev):
 @pytest.mark.parametrize("D,tokens,B", [(768, 197, 5), (128, 17, 9)])
 def test_gemm_qkv_rope(dev, D, tokens, B):
     from clipself_b200 import ops, _lib as L
-    from clipself_b200.tower import rope_tables
+    from clipself_b200.tower import rope_tables, rope_vectors
     M, N, K = B * tokens, 3 * D, D
     a, w = _mk(M, N, K, dev, seed=3)
     bias = torch.randn(N, device=dev)
@@ -90,7 +90,8 @@ def test_gemm_qkv_rope(dev, D, tokens, B):
     cos, sin = rope_tables(g, 64, 16)
     cos, sin = cos.to(dev), sin.to(dev)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    ops.gemm(a, w, out, mode=L.EPI_QKV_ROPE, bias=bias, rope=(cos, sin), tokens=tokens, rope_cols=2 * D)
+    pos, freq = (t.to(dev) for t in rope_vectors(g, 64, 16))
+    ops.gemm(a, w, out, mode=L.EPI_QKV_ROPE, bias=bias, rope=(pos, freq), tokens=tokens, rope_cols=2 * D)
     y = (a.float() @ w.float().t() + bias).view(B, tokens, 3, D // 64, 64)
     ref = y.clone()
     t = y[:, 1:, :2]                                   # patch tokens, q and k
