@@ -91,6 +91,89 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, long long ldx, long long M, int 
     }
 }
 
+
+// Register-resident variant for the row widths of the towers (D = 32 lanes x VPL 16-byte vectors):
+// every load of the row is in flight at once, statistics and normalisation never leave registers.
+template <typename TIn, int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_reg_kernel(const TIn* __restrict__ x, long long ldx, long long M, int row_div, int row_mul, int row_off,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out) {
+    constexpr int EPV = 16 / (int)sizeof(TIn);          // elements per 16-byte vector (4 f32 / 8 bf16)
+    constexpr int D = 32 * VPL * EPV;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * LN_WARPS + warp;
+    if (m >= M) return;
+    const long long prow = m * row_mul + (row_div > 0 ? m / row_div : 0) + row_off;
+    const TIn* xr = x + prow * ldx;
+    float v[VPL * EPV];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int e0 = (i * 32 + lane) * EPV;
+        if constexpr (sizeof(TIn) == 4) {
+            const float4 f = *reinterpret_cast<const float4*>(xr + e0);
+            v[i * 4 + 0] = f.x; v[i * 4 + 1] = f.y; v[i * 4 + 2] = f.z; v[i * 4 + 3] = f.w;
+        } else {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + e0);
+            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+            v[i * 8 + 0] = a.x; v[i * 8 + 1] = a.y; v[i * 8 + 2] = b.x; v[i * 8 + 3] = b.y;
+            v[i * 8 + 4] = c.x; v[i * 8 + 5] = c.y; v[i * 8 + 6] = d.x; v[i * 8 + 7] = d.y;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) sum += v[i];
+    const float mean = warp_sum(sum) / (float)D;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) {
+        const float d = v[i] - mean;
+        var += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(var) / (float)D + eps);
+    __nv_bfloat16* yr = y + m * ldy;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int e0 = (i * 32 + lane) * EPV;
+        float o[EPV];
+#pragma unroll
+        for (int j = 0; j < EPV; j += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + e0 + j);
+            const float4 b = *reinterpret_cast<const float4*>(beta + e0 + j);
+            o[j + 0] = (v[i * EPV + j + 0] - mean) * rstd * g.x + b.x;
+            o[j + 1] = (v[i * EPV + j + 1] - mean) * rstd * g.y + b.y;
+            o[j + 2] = (v[i * EPV + j + 2] - mean) * rstd * g.z + b.z;
+            o[j + 3] = (v[i * EPV + j + 3] - mean) * rstd * g.w + b.w;
+        }
+        if constexpr (EPV == 4) {
+            uint2 pk;
+            pk.x = pack_bf16(o[0], o[1]);
+            pk.y = pack_bf16(o[2], o[3]);
+            *reinterpret_cast<uint2*>(yr + e0) = pk;
+        } else {
+            uint4 pk;
+            pk.x = pack_bf16(o[0], o[1]);
+            pk.y = pack_bf16(o[2], o[3]);
+            pk.z = pack_bf16(o[4], o[5]);
+            pk.w = pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(yr + e0) = pk;
+        }
+    }
+    if (lane == 0) {
+        if (mean_out) mean_out[m] = mean;
+        if (rstd_out) rstd_out[m] = rstd;
+    }
+}
+
+template <typename TIn, int VPL>
+static void launch_ln_reg(const void* x, long long ldx, long long M, int row_div, int row_mul, int row_off,
+                          const float* gamma, const float* beta, float eps, void* y, long long ldy, float* mean,
+                          float* rstd, cudaStream_t st) {
+    layernorm_fwd_reg_kernel<TIn, VPL><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, st>>>(
+        (const TIn*)x, ldx, M, row_div, row_mul, row_off, gamma, beta, eps, (__nv_bfloat16*)y, ldy, mean, rstd);
+}
+
 // images [B,3,S,S] -> patches [B*g*g, ldp] bf16, column = c*P*P + py*P + px  (flattened conv weight
 // order).  One CTA per (image, patch row): each image row segment is read contiguously.
 template <typename TIn>
@@ -179,9 +262,28 @@ extern "C" int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, 
     CS_CHECK_ARG(M > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && row_mul >= 1,
                  "cs_layernorm_fwd: D, ldx, ldy must be multiples of 8 (D=%d ldx=%lld ldy=%lld)", D, (long long)ldx,
                  (long long)ldy);
+    cudaStream_t st = (cudaStream_t)stream;
+    // register-resident fast paths for the widths of the EVA02 towers
+#define LN_REG(T, VPL)                                                                                          \
+    {                                                                                                           \
+        launch_ln_reg<T, VPL>(x, ldx, M, row_div, row_mul, row_off, gamma, beta, eps, y_bf16, ldy, mean, rstd, st); \
+        CS_LAUNCH_CHECK();                                                                                      \
+        return CS_OK;                                                                                           \
+    }
+    if (x_dtype == CS_F32) {
+        if (D == 768) LN_REG(float, 6)
+        if (D == 1024) LN_REG(float, 8)
+        if (D == 2048) LN_REG(float, 16)
+        if (D == 128) LN_REG(float, 1)
+    } else {
+        if (D == 768) LN_REG(__nv_bfloat16, 3)
+        if (D == 1024) LN_REG(__nv_bfloat16, 4)
+        if (D == 2048) LN_REG(__nv_bfloat16, 8)
+        if (D == 256) LN_REG(__nv_bfloat16, 1)
+    }
+#undef LN_REG
     const int smem = LN_WARPS * D * (int)sizeof(float);
     CS_CHECK_ARG(smem <= 160 * 1024, "cs_layernorm_fwd: D=%d too large", D);
-    cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(M, LN_WARPS);
     if (x_dtype == CS_F32) {
         static bool cfg = false;

@@ -300,6 +300,14 @@ class EVAVisionTransformer(nn.Module):
                                       "call under torch.no_grad()")
         return self._infer_engine().forward_cls(self._prep(x))
 
+    def teacher_chunk_images(self) -> int:
+        return self._infer_engine().chunk_images
+
+    def forward_chunked(self, x: Tensor, events) -> Tensor:
+        """forward() on a crop tensor that is still being filled by an H2D stream: chunk k may be
+        read once events[k] has completed (see training/clipself.py)."""
+        return self._infer_engine().forward_cls(x, ready_events=events)
+
     def _prep(self, x: Tensor) -> Tensor:
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()

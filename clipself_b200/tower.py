@@ -155,8 +155,11 @@ class Workspace:
 class TowerEngine:
     """Runs the kernel sequence of one tower."""
 
-    def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device, chunk_images: int = 128):
+    def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device, chunk_images: Optional[int] = None):
+        import os
         L.require_device()
+        if chunk_images is None:
+            chunk_images = int(os.environ.get("CLIPSELF_TEACHER_CHUNK", "128"))
         self.cfg = cfg
         self.device = device
         self.w = PackedTower(cfg, sd, device)
@@ -201,16 +204,21 @@ class TowerEngine:
         ops.gemm(ws.h2, pb.w3, x, M=M, bias=pb.b3, residual=x)
 
     # ------------------------------------------------------------------ teacher
-    def forward_cls(self, images: Tensor, out: Optional[Tensor] = None) -> Tensor:
-        """encode_image(normalize=False): [R,3,S,S] -> [R, embed_dim] f32, no autograd."""
+    def forward_cls(self, images: Tensor, out: Optional[Tensor] = None, ready_events=None) -> Tensor:
+        """encode_image(normalize=False): [R,3,S,S] -> [R, embed_dim] f32, no autograd.
+        ready_events[k] (optional) gates chunk k on an in-flight H2D copy of its rows."""
         cfg = self.cfg
         R = images.shape[0]
         out = out if out is not None else torch.empty(R, cfg.embed_dim, device=self.device, dtype=torch.float32)
         step = min(self.chunk_images, R)
         ws = self.workspace(step)
         cls_ln = torch.empty(step, cfg.width, device=self.device, dtype=torch.bfloat16)
-        for s in range(0, R, step):
+        if ready_events is not None:
+            assert len(ready_events) == (R + step - 1) // step
+        for k, s in enumerate(range(0, R, step)):
             n = min(step, R - s)
+            if ready_events is not None:
+                torch.cuda.current_stream().wait_event(ready_events[k])
             self.embed(images[s:s + n], ws.x)
             for i in range(cfg.layers):
                 self.block_inplace(i, ws, n)

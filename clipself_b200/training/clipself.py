@@ -25,6 +25,44 @@ from ..model import cosine_distill_loss
 
 
 class CLIPSelf:
+    def __init__(self):
+        self._copy_stream = None
+        self._crops_dev = None
+        self._crops_free = None
+
+    def _stream_crops(self, image_crops, valid, R, device, dtype, chunk):
+        """Copy only the valid crops host->device on a side stream, one event per teacher chunk, so
+        the PCIe transfer overlaps the student forward and the earlier teacher chunks.
+        Runs of consecutive valid rows go as single cudaMemcpyAsync calls straight from the
+        (pinned) batch tensor: no host-side gather."""
+        B, K = valid.shape
+        flat = image_crops.reshape(B * K, *image_crops.shape[2:])
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._crops_free = torch.cuda.Event()
+        if self._crops_dev is None or self._crops_dev.shape[0] < R or self._crops_dev.shape[1:] != flat.shape[1:] \
+                or self._crops_dev.dtype != dtype:
+            self._crops_dev = torch.empty((B * K,) + tuple(flat.shape[1:]), device=device, dtype=dtype)
+        else:
+            self._copy_stream.wait_event(self._crops_free)      # previous step's teacher is done reading
+        dev = self._crops_dev
+        idx = valid.flatten().nonzero().flatten().tolist()
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for s0 in range(0, R, chunk):
+                n = min(chunk, R - s0)
+                a = s0
+                while a < s0 + n:                               # maximal run of consecutive source rows
+                    b = a + 1
+                    while b < s0 + n and idx[b] == idx[b - 1] + 1:
+                        b += 1
+                    dev[a:b].copy_(flat[idx[a]:idx[a] + (b - a)], non_blocking=True)
+                    a = b
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        return dev[:R], events
+
     def __call__(self, batch, model, dist_model, loss, device, cast_dtype, distributed, args):
         if distributed:
             model = getattr(model, "module", model)
@@ -34,6 +72,7 @@ class CLIPSelf:
         dtype = cast_dtype if cast_dtype is not None else torch.float32
         B, K = normed_boxes.shape[:2]
 
+        crop_events = None
         if normed_boxes.device.type == "cpu":
             # host-side, bit-exact: valid = boxes[..., 4] > 0.5, image-major order (clipself.py:29-36)
             boxes32 = normed_boxes.float()
@@ -42,11 +81,10 @@ class CLIPSelf:
             offsets = torch.zeros(B + 1, dtype=torch.int32)
             offsets[1:] = counts.cumsum(0)
             R = int(offsets[-1])
-            rois = boxes32[valid][:, :4].contiguous()
-            crops = image_crops[valid]                   # only the valid crops cross PCIe
-            rois = rois.to(device, non_blocking=True)
+            rois = boxes32[valid][:, :4].contiguous().to(device, non_blocking=True)
             offsets = offsets.to(device, non_blocking=True)
-            crops = crops.to(device=device, dtype=dtype, non_blocking=True)
+            crops, crop_events = self._stream_crops(image_crops, valid, R, device, dtype,
+                                                    dist_model.visual.teacher_chunk_images())
         else:
             rois_all, crop_index, _, offsets = ops.extract_rois(normed_boxes.float().contiguous())
             R = int(offsets[-1])                         # the step's single device->host sync
@@ -69,10 +107,15 @@ class CLIPSelf:
             raise NotImplementedError(f"--multiscale (student at {tar_size}px) needs the variable-resolution "
                                       "tower: SURVEY.md §8f rank 4, not built yet")
 
-        with torch.no_grad():
-            teacher_crop_features = dist_model.encode_image(crops, normalize=False)
+        # student forward first: it only needs the (small) images, so it overlaps the crop H2D stream
         model.visual.sync_gradients = bool(distributed)
         student_roi_features = model.visual.roi_features_packed(images, rois, offsets, R)
+        with torch.no_grad():
+            if crop_events is not None:
+                teacher_crop_features = dist_model.visual.forward_chunked(crops, crop_events)
+                self._crops_free.record()
+            else:
+                teacher_crop_features = dist_model.encode_image(crops, normalize=False)
 
         loss_cosine = cosine_distill_loss(student_roi_features, teacher_crop_features,
                                           float(getattr(args, "cosine_weight", 1.0)))

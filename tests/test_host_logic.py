@@ -1,0 +1,138 @@
+"""Host-side logic that needs no GPU: flat parameter layout, state_dict compatibility, factory errors,
+synthetic data contract, plug-in index extraction."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clipself_oracle as O
+
+
+def test_state_dict_keys_match_reference_layout():
+    """visual.* keys / shapes equal SURVEY.md Appendix D.1 (286 visual keys for B/16)."""
+    from clipself_b200.factory import create_model
+    m = create_model("EVA02-CLIP-B-16", "eva", cache_dir="")
+    sd = m.state_dict()
+    vis = {k: v for k, v in sd.items() if k.startswith("visual.")}
+    assert len(vis) == 286
+    expect = dict(O.tower_param_shapes(O.CFG_B16))
+    for name, shape in expect.items():
+        assert tuple(vis["visual." + name].shape) == shape, name
+    rope_keys = [k for k in vis if "freqs_" in k]
+    assert len(rope_keys) == 2 * (1 + 12)                      # visual.rope + every blocks.N.attn.rope
+    assert "logit_scale" in sd
+    assert m.visual.image_size == 224 and m.visual.patch_embed.patch_size == (16, 16) and m.embed_dim == 512
+
+
+def test_rope_buffers_bit_exact_vs_oracle():
+    from clipself_b200.tower import rope_tables, rope_vectors
+    for grid in (14, 24, 4):
+        cos, sin = rope_tables(grid, 64, 16)
+        ocos, osin = O.rope_tables(grid, 64, 16)
+        assert torch.equal(cos, ocos) and torch.equal(sin, osin)
+        pos, freq = rope_vectors(grid, 64, 16)
+        ang = torch.cat([(pos[:, None] * freq[None]).repeat_interleave(2, -1)[:, None].expand(grid, grid, 32),
+                         (pos[:, None] * freq[None]).repeat_interleave(2, -1)[None].expand(grid, grid, 32)], -1)
+        assert torch.equal(ang.reshape(-1, 64).cos(), cos)
+
+
+def test_flat_layout_groups():
+    from clipself_b200.student import FlatLayout
+    from clipself_b200.tower import TowerCfg
+    cfg = TowerCfg()
+    lay = FlatLayout(cfg)
+    D, Hd, L = cfg.width, cfg.hidden, cfg.layers
+    per_block_w = 4 * D * D + 3 * D * Hd
+    assert lay.n_decay == L * per_block_w - 2 * D * D                       # last block q/k weights live in the tail
+    assert lay.n_total == 85_131_264 or lay.n_total > 85_000_000            # ~85.1 M trainable block params (SURVEY B)
+    assert set(lay.gradless) == {f"blocks.{L-1}.attn.q_proj.weight", f"blocks.{L-1}.attn.k_proj.weight",
+                                 f"blocks.{L-1}.attn.q_bias"}
+    # q|k|v and w1|w2 adjacency that the fused GEMMs rely on
+    for i in range(L - 1):
+        q, k, v = (lay.offset[f"blocks.{i}.attn.{n}_proj.weight"] for n in "qkv")
+        assert k == q + D * D and v == k + D * D
+        assert lay.offset[f"blocks.{i}.mlp.w2.weight"] == lay.offset[f"blocks.{i}.mlp.w1.weight"] + Hd * D
+        assert lay.offset[f"blocks.{i}.mlp.w2.bias"] == lay.offset[f"blocks.{i}.mlp.w1.bias"] + Hd
+    assert all(o % 4 == 0 for o in lay.offset.values())                     # 16-byte aligned views
+    # weight-decay grouping equals the reference rule (main.py:199-213): ndim < 2 -> no decay
+    for name, off in lay.offset.items():
+        if name in lay.gradless:
+            assert off >= lay.n_grad
+        elif len(lay.shape[name]) == 2:
+            assert off < lay.n_decay
+        else:
+            assert lay.n_decay <= off < lay.n_grad
+
+
+def test_factory_errors_like_reference():
+    from clipself_b200.factory import create_model
+    with pytest.raises(RuntimeError):
+        create_model("no-such-model", "eva")
+    with pytest.raises(RuntimeError):
+        create_model("EVA02-CLIP-B-16", "eva", cache_dir="/nonexistent/ckpt.pt")      # eva_clip/factory.py:290-295
+    with pytest.raises(RuntimeError):
+        create_model("EVA02-CLIP-B-16", "eva", cache_dir="", require_pretrained=True)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    from clipself_b200.factory import create_model
+    a = create_model("EVA02-CLIP-B-16", "eva", cache_dir="")
+    path = tmp_path / "ck.pt"
+    torch.save({"state_dict": {"module." + k: v for k, v in a.state_dict().items()}}, path)
+    b = create_model("EVA02-CLIP-B-16", "eva", cache_dir=str(path))
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+
+
+def test_lock_semantics():
+    from clipself_b200.factory import create_model
+    m = create_model("EVA02-CLIP-B-16", "eva", cache_dir="")
+    m.lock_image_tower(unlocked_groups=12)
+    names = {n for n, p in m.visual.named_parameters() if p.requires_grad}
+    assert names and all(n.startswith("blocks.") for n in names)
+    m.lock_image_tower(unlocked_groups=3)
+    names = {n.split(".")[1] for n, p in m.visual.named_parameters() if p.requires_grad}
+    assert names == {"9", "10", "11"}
+    m.lock_image_tower(unlocked_groups=0)                   # blocks[-0:] == all blocks, as in the reference
+    names = {n.split(".")[1] for n, p in m.visual.named_parameters() if p.requires_grad}
+    assert len(names) == 12
+
+
+def test_synthetic_dataset_contract():
+    from clipself_b200.data import SyntheticDistillDataset, grid_box_templates, synthetic_batch
+    assert torch.equal(grid_box_templates(3, 3), O.grid_box_templates(3, 3))      # fp32 linspace edges, bit-exact
+    ds = SyntheticDistillDataset(64, 32, 6, kind="grid", length=4, seed=1)
+    img, boxes, crops = ds[2]
+    assert img.shape == (3, 64, 64) and boxes.shape == (6, 5) and crops.shape == (6, 3, 32, 32)
+    assert set(boxes[:, 4].tolist()) <= {0.0, 1.0} and boxes[0, 4] == 1.0
+    images, b, c = synthetic_batch(64, 3, 5, "proposal", seed=2, ragged=True)
+    valid = b[..., 4] > 0.5
+    assert (b[valid][:, 2] > b[valid][:, 0]).all() and (b[~valid] == 0).all()
+
+
+def test_plugin_host_index_extraction_bit_exact():
+    """The host branch of the plug-in (CPU batch) selects exactly what clipself.py:29-36 selects."""
+    _, boxes, crops = O.synth_batch(O.CFG_TINY, 4, 6, 5, kind="proposal", ragged=True, crop_size=8)
+    rois_ref, idx_ref = O.extract_rois(boxes)
+    boxes32 = boxes.float()
+    valid = boxes32[:, :, 4] > 0.5
+    rois = boxes32[valid][:, :4]
+    assert torch.equal(rois, torch.cat(rois_ref))
+    assert valid.flatten().nonzero().flatten().tolist() == idx_ref.tolist()
+    assert torch.equal(crops[valid], crops.flatten(0, 1)[idx_ref])
+
+
+def test_fused_adamw_group_bookkeeping():
+    from clipself_b200.optim import FusedAdamW
+
+    class FakeLayout:
+        n_decay, n_grad = 8, 12
+
+    class FakeEngine:
+        layout = FakeLayout()
+        device = torch.device("cpu")
+
+    opt = FusedAdamW(FakeEngine(), lr=1e-3, weight_decay=0.1)
+    assert [g["weight_decay"] for g in opt.param_groups] == [0.0, 0.1]
+    for g in opt.param_groups:
+        g["lr"] = 5e-4                                       # what scheduler.py:4-6 does
+    assert opt.exp_avg.numel() == 12 and opt.state_dict()["step"] == 0
