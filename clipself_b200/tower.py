@@ -159,7 +159,7 @@ class TowerEngine:
         import os
         L.require_device()
         if chunk_images is None:
-            chunk_images = int(os.environ.get("CLIPSELF_TEACHER_CHUNK", "128"))
+            chunk_images = int(os.environ.get("CLIPSELF_TEACHER_CHUNK", "256"))
         self.cfg = cfg
         self.device = device
         self.w = PackedTower(cfg, sd, device)
