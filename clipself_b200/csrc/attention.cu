@@ -6,6 +6,8 @@
 // online softmax in f32 (exp2 domain).  Tensor-core path here is mma.sync (legacy HMMA) — the
 // attention contractions are ~4 % (B/16) of the tower FLOPs; the tcgen05 rewrite is tracked in
 // DESIGN.md §roadmap.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cs {
@@ -527,12 +529,24 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 }  // namespace attn
 }  // namespace cs
 
+namespace cs {
+int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
+}
+
 extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
                                 float* lse, void* stream) {
     using namespace cs;
     using namespace cs::attn;
     CS_CHECK_ARG(qkv_bf16 && out_bf16, "cs_attention_fwd: null pointer");
     CS_CHECK_ARG(B > 0 && N > 0 && H > 0, "cs_attention_fwd: bad shape");
+    {
+        // tcgen05 kernel for N <= 224 (B/16: 197 tokens); longer sequences use the streaming kernel below
+        static const bool legacy = getenv("CS_ATTN_LEGACY") != nullptr;
+        if (!legacy) {
+            const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, (cudaStream_t)stream);
+            if (rc != CS_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const long long blocks = (long long)B * H * ceil_div(N, BQ);
     CS_CHECK_ARG(blocks < (1ll << 31), "cs_attention_fwd: grid too large");
     dim3 grid((unsigned)blocks);
