@@ -22,7 +22,8 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("mode", C.c_int32), ("out_dtype", C.c_int32), ("out", vp), ("ldo", i64),
                 ("bias", vp), ("residual", vp), ("ldr", i64), ("rope_pos", vp), ("rope_freq", vp),
                 ("rope_grid", C.c_int32), ("tokens", C.c_int32), ("rope_cols", C.c_int32), ("pos_embed", vp),
-                ("alpha", f32), ("reserved", C.c_int32)]
+                ("alpha", f32), ("reserved", C.c_int32), ("ln_stats", vp), ("ln_c1", vp), ("ln_parts", C.c_int32),
+                ("ln_dim", C.c_int32), ("ln_eps", f32), ("reserved2", C.c_int32), ("stats_out", vp)]
 
 
 # name -> argtypes, exactly the prototypes of include/clipself_b200.h
@@ -43,7 +44,7 @@ PROTOTYPES = {
     "cs_layernorm_fwd": [vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, f32, vp, i64, vp, vp, vp],
     "cs_gemm_bf16": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],
     "cs_pack_swiglu_weights": [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp],
-    "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp],
+    "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp, vp],
     "cs_cast_pad_bf16": [vp, i64, i64, i64, vp, i64, vp],
     "cs_attention_bwd": [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp],
     "cs_cast_transpose_bf16": [vp, i32, i64, i32, i64, vp, i64, vp, i64, vp],

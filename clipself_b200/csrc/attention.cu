@@ -530,11 +530,12 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 }  // namespace cs
 
 namespace cs {
-int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
+int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
+                     cudaStream_t st);
 }
 
 extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
-                                float* lse, void* stream) {
+                                float* lse, float* row_stats, void* stream) {
     using namespace cs;
     using namespace cs::attn;
     CS_CHECK_ARG(qkv_bf16 && out_bf16, "cs_attention_fwd: null pointer");
@@ -543,9 +544,10 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
         // tcgen05 kernel for N <= 224 (B/16: 197 tokens); longer sequences use the streaming kernel below
         static const bool legacy = getenv("CS_ATTN_LEGACY") != nullptr;
         if (!legacy) {
-            const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, (cudaStream_t)stream);
+            const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
+        CS_CHECK_ARG(row_stats == nullptr, "cs_attention_fwd: row_stats is only produced by the N <= 224 kernel");
     }
     const long long blocks = (long long)B * H * ceil_div(N, BQ);
     CS_CHECK_ARG(blocks < (1ll << 31), "cs_attention_fwd: grid too large");

@@ -4,8 +4,9 @@
 //   MN-major straight from its [key][dim] layout)  ->  O / rowsum -> bf16.
 // Replaces xformers.memory_efficient_attention at eva_vit_model.py:206-217 for the teacher's crops.
 //
-// Persistent CTA per SM, 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
-// warps 2-5 softmax + epilogue.  Work item = one (image, head); its K and V tiles are loaded once and
+// Persistent CTA per SM, 320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
+// warps 2-9 softmax + epilogue: two warps per TMEM lane quarter split each row's key columns (and the
+// output dims), exchanging row max / row sum through shared memory.  Work item = one (image, head); its K and V tiles are loaded once and
 // reused by the ceil(N/128) query tiles.  S is double buffered in TMEM so Q K^T of the next tile runs
 // under the softmax of the current one.
 #include "tc_common.cuh"
@@ -16,7 +17,7 @@ using namespace cs::tc;
 
 constexpr int HD = 64;
 constexpr int BM = 128;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;           // TMA warp, MMA warp, 8 softmax/epilogue warps (two per TMEM lane quarter)
 constexpr int Q_BYTES = BM * 128;
 constexpr int P_ATOM_BYTES = BM * 128;      // [128 rows][64 keys] bf16, SWIZZLE_128B K-major
 constexpr int MAX_NKP = 224;
@@ -45,6 +46,7 @@ struct Params {
     float scale_log2, scale;
     __nv_bfloat16* out;
     float* lse;
+    float* row_stats;               // optional [B*N, 2H, 2]: per (row, head, dim-half) sum and sum of squares of the bf16 output
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -72,6 +74,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     auto s_empty = [&](int s) { return bar + 8u * (10 + s); };
     const uint32_t p_full = bar + 8u * 12, p_empty = bar + 8u * 13, o_full = bar + 8u * 14, o_empty = bar + 8u * 15;
     const uint32_t tmem_slot = bar + 8u * 16;
+    float* xch = reinterpret_cast<float*>(smem + (bar - base) + 8 * 18);   // [2 halves][128 rows] max, then sums
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,12 +93,12 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 1);
             mbar_init(s_full(s), 1);
-            mbar_init(s_empty(s), 128);
+            mbar_init(s_empty(s), 256);
         }
-        mbar_init(p_full, 128);
+        mbar_init(p_full, 256);
         mbar_init(p_empty, 1);
         mbar_init(o_full, 1);
-        mbar_init(o_empty, 128);
+        mbar_init(o_empty, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -169,9 +172,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     } else {
         // ------------------------------ softmax + epilogue ------------------------
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;                          // 0: first half of the key chunks, 1: the rest
         const int r = quarter * 32 + lane;                         // row of the tile owned by this thread
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const int nchunks = (p.nkp + 31) / 32;
+        const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
+        const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+        float* xmax = xch;                                         // [2][128]
+        float* xsum = xch + 256;                                   // [2][128]
         for (int tt = 0; tt < total_tiles; ++tt) {
             const int il = tt / p.ntm, mt = tt % p.ntm;
             const int item = blockIdx.x + il * gridDim.x;
@@ -179,9 +187,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             mbar_wait(s_full(tt & 1), (uint32_t)(tt >> 1) & 1u);
             tc_fence_after();
             const uint32_t ts = tmem_base + lane_addr + (uint32_t)((tt & 1) * S_STRIDE);
-            // pass 1: row max over the valid keys
+            // pass 1: row max over this thread's share of the valid keys
             float mx = -INFINITY;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[32];
                 tmem_ld32(ts + c * 32, v);
                 tmem_ld_wait();
@@ -189,11 +197,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 for (int j = 0; j < 32; ++j)
                     if (c * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
             }
+            xmax[half * 128 + r] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(xmax[r], xmax[128 + r]);
             const float mxs = mx * p.scale_log2;
             // P buffer must have been consumed by the previous tile's PV
             mbar_wait(p_empty, ((uint32_t)tt & 1u) ^ 1u);
             float sum = 0.f;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[32];
                 tmem_ld32(ts + c * 32, v);
                 tmem_ld_wait();
@@ -215,44 +226,51 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     *reinterpret_cast<uint4*>(sP_ptr + (kb8 >> 3) * P_ATOM_BYTES + r * 128 + (((kb8 & 7) ^ (r & 7)) << 4)) = pk;
                 }
             }
+            xsum[half * 128 + r] = sum;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
             tc_fence_before();
             mbar_arrive(p_full);
             mbar_arrive(s_empty(tt & 1));
-            // epilogue: O / sum
+            // epilogue: O / sum; this warp converts 32 of the 64 output dims
             mbar_wait(o_full, (uint32_t)tt & 1u);
             tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld32(tmem_base + lane_addr + O_COL, o0);
-            tmem_ld32(tmem_base + lane_addr + O_COL + 32, o1);
+            uint32_t o[32];
+            tmem_ld32(tmem_base + lane_addr + O_COL + half * 32, o);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(o_empty);
+            // o_full implies every softmax thread passed p_full, i.e. both halves of xsum are written
+            sum = xsum[r] + xsum[128 + r];
             const int row = mt * BM + r;
             if (row < p.N) {
                 const float inv = 1.0f / sum;
-                __nv_bfloat16* dst = p.out + ((long long)b * p.N + row) * D + h * HD;
+                __nv_bfloat16* dst = p.out + ((long long)b * p.N + row) * D + h * HD + half * 32;
+                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint4 pk;
-                    pk.x = pack_bf16(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
-                    pk.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
-                    pk.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
-                    pk.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+                    pk.x = pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                    pk.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                    pk.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                    pk.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
                     *reinterpret_cast<uint4*>(dst + 8 * i) = pk;
-                }
+                    if (p.row_stats != nullptr) {
+                        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 pk;
-                    pk.x = pack_bf16(__uint_as_float(o1[8 * i]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
-                    pk.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
-                    pk.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
-                    pk.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + 32 + 8 * i) = pk;
+                        for (int z = 0; z < 4; ++z) {
+                            const float2 f = unpack_bf16(w4[z]);   // statistics of the values as stored
+                            s1 += f.x + f.y;
+                            s2 += f.x * f.x + f.y * f.y;
+                        }
+                    }
                 }
-                if (p.lse != nullptr)
+                if (p.row_stats != nullptr)
+                    *reinterpret_cast<float2*>(p.row_stats + (((long long)b * p.N + row) * (2 * p.H) + 2 * h + half) * 2) = make_float2(s1, s2);
+                if (p.lse != nullptr && half == 0)
                     p.lse[((long long)b * p.H + h) * p.N + row] = mx * p.scale + logf(sum);
             }
+            // xmax / xsum are rewritten by the next tile only after its bar.sync / p_full round
+            asm volatile("bar.sync 2, 256;" ::: "memory");
         }
     }
     tc_fence_before();
@@ -264,7 +282,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 
 // Returns CS_ERR_UNSUPPORTED (without setting up anything) when the shape is outside this kernel's
 // envelope; cs_attention_fwd then uses the generic mma.sync kernel.
-int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st) {
+int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
+                     cudaStream_t st) {
     using namespace attn_tc;
     if (N > MAX_NKP || N < 1) return CS_ERR_UNSUPPORTED;
     const int nkp = ceil_div(N, 16) * 16;
@@ -282,8 +301,9 @@ int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* ou
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
+    p.row_stats = row_stats;
     const int n_atoms = (nkp + 63) / 64;
-    const int smem = 2 * Q_BYTES + 4 * nkp * 128 + n_atoms * P_ATOM_BYTES + 256 + 1024;
+    const int smem = 2 * Q_BYTES + 4 * nkp * 128 + n_atoms * P_ATOM_BYTES + 256 + 2048 + 1024;   // + barriers, exchange, align
     static int configured = 0;
     if (configured < smem) {
         CS_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -33,7 +33,8 @@ struct Cfg {
     static constexpr int BAR_BYTES = 256;
     static constexpr int EPI_TILE_BYTES = 32 * 128;          // one swizzled 32-row x 128 B staging tile per warp
     static constexpr int EPI_BIAS_BYTES = BLOCK_N * 4;       // this tile's bias slice, one private copy per warp
-    static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + EPI_BIAS_BYTES;
+    static constexpr int EPI_ROWSTAT_BYTES = 256;            // (mean, rstd) of this warp's 32 rows (LN folding)
+    static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + 2 * EPI_BIAS_BYTES + EPI_ROWSTAT_BYTES;  // bias + ln_c1
     static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
     static constexpr int ROPE_BYTES = 512;                   // 64 grid positions + 16 frequencies (+pad)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + ROPE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
@@ -55,19 +56,27 @@ struct EpiParams {
     const float* pos_embed;
     float alpha;
     int dbg;   // debug switches for epilogue ablations (cs_gemm_epilogue_t.reserved); 0 in production
+    const float* ln_stats;   // LayerNorm folding (see cs_gemm_epilogue_t)
+    const float* ln_c1;
+    int ln_parts;
+    float ln_inv_dim;
+    float ln_eps;
+    float* stats_out;        // SWIGLU: per (row, tile) partial sum / sumsq of the bf16 outputs
+    int k_splits;            // split-K factor (RES_RED accumulate into a zeroed output), 1 = off
+    int kb_per_split;
 };
 
 enum ResKind { RES_NONE = 0, RES_LOAD = 1, RES_RED = 2 };
 
 // one epilogue warp: 32 accumulator rows of one tile
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t taddr, int mw, int n0, int M, int N,
-                                              uint8_t* st, float* sbias, const float* srope, int lane) {
+                                              uint8_t* st, float* sbias, const float* srope, int lane, bool use_bias) {
     using C = Cfg<BLOCK_N>;
     const int crow = lane >> 3;                   // coalesced phase: row within a group of 4
     const int cchunk = lane & 7;                  // coalesced phase: 16 B chunk of the 128 B row slice
     // this tile's bias slice -> private smem copy (replaces dependent global loads in the hot loop)
-    if (ep.bias != nullptr) {
+    if (ep.bias != nullptr && use_bias) {
 #pragma unroll
         for (int j = lane * 4; j < BLOCK_N; j += 128) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -77,6 +86,32 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
     } else {
 #pragma unroll
         for (int j = lane * 4; j < BLOCK_N; j += 128) *reinterpret_cast<float4*>(sbias + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* sc1 = sbias + BLOCK_N;
+    float* srow = sc1 + BLOCK_N;
+    if constexpr (LNFOLD) {
+#pragma unroll
+        for (int j = lane * 4; j < BLOCK_N; j += 128) {
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + j < N) c = *reinterpret_cast<const float4*>(ep.ln_c1 + n0 + j);
+            *reinterpret_cast<float4*>(sc1 + j) = c;
+        }
+        // (mean, rstd) of input row mw + lane from its partial sums
+        float mu = 0.f, rs = 0.f;
+        if (mw + lane < M) {
+            const float* ps = ep.ln_stats + (long long)(mw + lane) * ep.ln_parts * 2;
+            float s1 = 0.f, s2 = 0.f;
+            for (int q = 0; q < ep.ln_parts; q += 2) {
+                const float4 v = *reinterpret_cast<const float4*>(ps + q * 2);
+                s1 += v.x + v.z;
+                s2 += v.y + v.w;
+            }
+            mu = s1 * ep.ln_inv_dim;
+            const float var = fmaxf(s2 * ep.ln_inv_dim - mu * mu, 0.f);
+            rs = rsqrtf(var + ep.ln_eps);
+        }
+        srow[lane * 2] = mu;
+        srow[lane * 2 + 1] = rs;
     }
     __syncwarp();
 
@@ -95,6 +130,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
         constexpr int OUT_COLS = (MODE == CS_EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N;
         const int out_n0 = (MODE == CS_EPI_SWIGLU) ? (n0 >> 1) : n0;
         const int out_N = (MODE == CS_EPI_SWIGLU) ? (N >> 1) : N;
+        float st1 = 0.f, st2 = 0.f;                          // SWIGLU stats_out: row sum / sum of squares of the stored values
 #pragma unroll 1
         for (int gc = 0; gc < OUT_COLS; gc += 64) {          // 64 bf16 output columns = 128 B per row
             if (out_n0 + gc >= out_N) break;
@@ -144,6 +180,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                     pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
                     const int chunk = half * 4 + j;
                     *reinterpret_cast<uint4*>(st + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+                    if constexpr (MODE == CS_EPI_SWIGLU) {
+                        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                        for (int z = 0; z < 4; ++z) {
+                            const float2 f = unpack_bf16(w4[z]);
+                            st1 += f.x + f.y;
+                            st2 += f.x * f.x + f.y * f.y;
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -161,6 +206,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)mm * ep.ldo + ocol) = val[i];
             }
             __syncwarp();
+        }
+        if constexpr (MODE == CS_EPI_SWIGLU) {
+            if (ep.stats_out != nullptr && m < M)
+                *reinterpret_cast<float2*>(ep.stats_out + ((long long)m * (N / BLOCK_N) + n0 / BLOCK_N) * 2) = make_float2(st1, st2);
         }
     } else {
         // ---------------- f32 outputs: raw staging, math in the coalesced phase ----------------
@@ -206,10 +255,19 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
             }
             __syncwarp();
             const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + cchunk * 4);
+            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (LNFOLD) c4 = *reinterpret_cast<const float4*>(sc1 + c + cchunk * 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = i * 4 + crow;
                 float4 f = *reinterpret_cast<const float4*>(st + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
+                if constexpr (LNFOLD) {
+                    const float2 ms = *reinterpret_cast<const float2*>(srow + rr * 2);      // (mean, rstd) of the input row
+                    f.x = ms.y * (f.x - ms.x * c4.x);
+                    f.y = ms.y * (f.y - ms.x * c4.y);
+                    f.z = ms.y * (f.z - ms.x * c4.z);
+                    f.w = ms.y * (f.w - ms.x * c4.w);
+                }
                 f.x += b4.x + extra[i].x;
                 f.y += b4.y + extra[i].y;
                 f.z += b4.z + extra[i].z;
@@ -229,7 +287,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
     }
 }
 
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             int M, int N, int K, const EpiParams ep) {
@@ -256,8 +314,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     const int num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m_tiles * num_n_tiles;
-    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int num_mn = num_m_tiles * num_n_tiles;
+    const int num_tiles = num_mn * ep.k_splits;          // split-K: tile t -> (mn = t % num_mn, split = t / num_mn)
+    const int num_kb_total = (K + BLOCK_K - 1) / BLOCK_K;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
@@ -290,9 +349,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n_tiles) * BLOCK_M;
-                const int n0 = (tile % num_n_tiles) * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int mn = tile % num_mn, sp = tile / num_mn;
+                const int m0 = (mn / num_n_tiles) * BLOCK_M;
+                const int n0 = (mn % num_n_tiles) * BLOCK_N;
+                const int kb0 = sp * ep.kb_per_split;
+                const int kb1 = min(num_kb_total, kb0 + ep.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + C::A_BYTES;
@@ -319,7 +381,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = (tile / num_mn) * ep.kb_per_split;
+                const int kb1 = min(num_kb_total, kb0 + ep.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);         // TMA bytes landed
                     tc_fence_after();
                     const uint32_t sa = base + stage * C::STAGE_BYTES;
@@ -330,10 +394,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr>>4)
                         umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                  (kb > 0 || k > 0) ? 1u : 0u);
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));             // frees the smem slot when MMAs retire
-                    if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+                    if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -349,15 +413,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         float* sbias = reinterpret_cast<float*>(st + C::EPI_TILE_BYTES);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / num_n_tiles) * BLOCK_M;
-            const int n0 = (tile % num_n_tiles) * BLOCK_N;
+            const int mn = tile % num_mn;
+            const int m0 = (mn / num_n_tiles) * BLOCK_M;
+            const int n0 = (mn % num_n_tiles) * BLOCK_N;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             if (!(ep.dbg & 8))
-                epilogue_tile<BLOCK_N, MODE, OUT_BF16, RES>(ep, taddr, m0 + quarter * 32, n0, M, N, st, sbias, srope, lane);
+                epilogue_tile<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD>(ep, taddr, m0 + quarter * 32, n0, M, N, st, sbias, srope, lane,
+                                                                    tile < num_mn);
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
@@ -371,19 +437,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // ----------------------------------------------------------------------------------------
 // Host side
 // ----------------------------------------------------------------------------------------
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD = false>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
                   cudaStream_t stream) {
     using C = Cfg<BLOCK_N>;
     static bool configured = false;
     if (!configured) {
-        CS_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES>,
+        CS_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+    gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -394,6 +460,7 @@ static int dispatch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, 
     switch (ep.mode) {
         case CS_EPI_STORE:
             if (ep.out_bf16) return launch<BLOCK_N, CS_EPI_STORE, true, RES_NONE>(ma, mb, M, N, K, ep, st);
+            if (res == RES_RED && ep.ln_stats != nullptr) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED, true>(ma, mb, M, N, K, ep, st);
             if (res == RES_RED) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED>(ma, mb, M, N, K, ep, st);
             if (res == RES_LOAD) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD>(ma, mb, M, N, K, ep, st);
             return launch<BLOCK_N, CS_EPI_STORE, false, RES_NONE>(ma, mb, M, N, K, ep, st);
@@ -445,6 +512,14 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     ep.pos_embed = e->pos_embed;
     ep.alpha = e->alpha;
     ep.dbg = e->reserved;
+    ep.ln_stats = e->ln_stats;
+    ep.ln_c1 = e->ln_c1;
+    ep.ln_parts = e->ln_parts;
+    ep.ln_inv_dim = e->ln_dim > 0 ? 1.0f / (float)e->ln_dim : 0.f;
+    ep.ln_eps = e->ln_eps;
+    ep.stats_out = e->stats_out;
+    ep.k_splits = 1;
+    ep.kb_per_split = ceil_div(K, BLOCK_K);
 
     bool use256 = (N % 256 == 0);
     if (e->mode == CS_EPI_SWIGLU) {
@@ -471,6 +546,36 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
         CS_CHECK_ARG(e->out_dtype == CS_F32 && e->mode == CS_EPI_STORE, "cs_gemm_bf16: residual needs f32 STORE output");
         res = (e->residual == e->out && e->ldr == e->ldo) ? RES_RED : RES_LOAD;
     }
-    CS_CHECK_ARG(e->mode != CS_EPI_STORE || e->out_dtype == CS_F32 || N % 64 == 0 || true, "unreachable");
+    if (e->ln_stats)
+        CS_CHECK_ARG(res == RES_RED && e->ln_c1 && e->ln_parts > 0 && e->ln_parts % 2 == 0 && e->ln_dim > 0 &&
+                         ((uintptr_t)e->ln_stats % 16 == 0) && ((uintptr_t)e->ln_c1 % 16 == 0),
+                     "cs_gemm_bf16: LN folding needs the in-place f32 residual epilogue, ln_c1, even ln_parts, ln_dim");
+    if (e->stats_out) CS_CHECK_ARG(e->mode == CS_EPI_SWIGLU, "cs_gemm_bf16: stats_out is a SWIGLU output");
+    if (e->reserved2 != 0) {
+        // split-K (reserved2 = requested splits, -1 = choose): partial products are accumulated with
+        // red.add into `out`, which the caller must have zeroed.  f32 STORE without residual only.
+        CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual == nullptr && e->ln_stats == nullptr,
+                     "cs_gemm_bf16: split-K needs a plain f32 STORE epilogue");
+        const int num_kb = ceil_div(K, BLOCK_K);
+        const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, use256 ? 256 : 128);
+        int best = 1;
+        if (e->reserved2 > 0) {
+            best = e->reserved2;
+        } else {
+            long long best_cost = -1;
+            for (int sp = 1; sp <= 8 && sp <= num_kb; ++sp) {
+                const long long waves = ceil_div((long long)tiles * sp, num_sms());
+                const long long cost = waves * (ceil_div(num_kb, sp) + 8);     // +8 k-blocks ~ per-tile epilogue/fill cost
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+            }
+        }
+        if (best > 1) {
+            ep.kb_per_split = ceil_div(num_kb, best);
+            ep.k_splits = ceil_div(num_kb, ep.kb_per_split);        // no empty split
+            ep.residual = reinterpret_cast<const float*>(ep.out);     // selects the red.add epilogue
+            ep.ldr = ep.ldo;
+            res = RES_RED;
+        }
+    }
     return use256 ? dispatch<256>(ma, mb, (int)M, N, K, ep, res, st) : dispatch<128>(ma, mb, (int)M, N, K, ep, res, st);
 }

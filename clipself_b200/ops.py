@@ -157,7 +157,8 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optio
          K: Optional[int] = None, mode: int = L.EPI_STORE, bias: Optional[Tensor] = None,
          residual: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, Tensor]] = None, tokens: int = 0,
          rope_cols: int = 0, pos_embed: Optional[Tensor] = None, alpha: float = 1.0,
-         ldo: Optional[int] = None, dbg: int = 0) -> Tensor:
+         ldo: Optional[int] = None, dbg: int = 0, ln_fold: Optional[Tuple[Tensor, Tensor, int, int, float]] = None,
+         stats_out: Optional[Tensor] = None, k_splits: int = 0) -> Tensor:
     """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16 row-major (lda/ldw = last dim)."""
     _chk(a, torch.bfloat16, "a")
     _chk(w, torch.bfloat16, "w")
@@ -180,6 +181,11 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optio
     e.pos_embed = _p(pos_embed)
     e.alpha = alpha
     e.reserved = dbg
+    if ln_fold is not None:          # (stats [M,parts,2], c1 [N], parts, dim, eps)
+        e.ln_stats, e.ln_c1 = _p(ln_fold[0]), _p(ln_fold[1])
+        e.ln_parts, e.ln_dim, e.ln_eps = int(ln_fold[2]), int(ln_fold[3]), float(ln_fold[4])
+    e.stats_out = _p(stats_out)
+    e.reserved2 = k_splits           # split-K (out must be pre-zeroed): -1 = let the library choose
     if GEMM_PROFILE is None:
         call("cs_gemm_bf16", _p(a), a.shape[-1], _p(w), w.shape[-1], M, N, K, C.byref(e), _stream())
         return out
@@ -201,9 +207,9 @@ def pack_swiglu_weights(w1: Tensor, w2: Tensor, b1: Tensor, b2: Tensor, ldk: int
 
 
 def attention_fwd(qkv: Tensor, B: int, N: int, H: int, scale: float, out: Tensor,
-                  lse: Optional[Tensor] = None) -> Tensor:
+                  lse: Optional[Tensor] = None, row_stats: Optional[Tensor] = None) -> Tensor:
     _chk(qkv, torch.bfloat16, "qkv")
-    call("cs_attention_fwd", _p(qkv), B, N, H, float(scale), _p(out), _p(lse), _stream())
+    call("cs_attention_fwd", _p(qkv), B, N, H, float(scale), _p(out), _p(lse), _p(row_stats), _stream())
     return out
 
 

@@ -318,6 +318,7 @@ class StudentEngine:
         ops.cast_transpose(t.d_head, Mp, cfg.embed_dim, dst=t.d_head_bf)
         d_tok = t.g_D2[:Mp]
         ops.gemm(t.d_head_bf, self.head_wT, d_tok, M=Mp)
+        self.flat_grad[:self.layout.n_decay].zero_()                 # split-K wgrad GEMMs accumulate with red.add
         dx = t.dx
         dx.zero_()                                                     # CLS rows get no gradient from the tail
         ops.layernorm_bwd_dx(d_tok, t.x[cfg.layers], Mp, D, t.tok_stats[0], t.tok_stats[1], fr.norm_g, dx,
@@ -329,7 +330,7 @@ class StudentEngine:
             ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
             ops.col_reduce(dx, M, D, self.g(i, "mlp.w3.bias"), ws)
             ops.cast_transpose(t.hln[i], M, Hd, dst_t=t.act_T_Hd)
-            ops.gemm(t.g_T_D, t.act_T_Hd, self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M)           # dW3 = dx^T hln
+            ops.gemm(t.g_T_D, t.act_T_Hd, self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M, k_splits=-1)           # dW3 = dx^T hln
             ops.gemm(t.g_bf_D, pk.w3T, t.g_Hd, M=M)                                               # d_hln
             ops.col_reduce(t.g_Hd, M, Hd, self.g(i, "mlp.ffn_ln.bias"), ws, x=t.h[i], mean=st[6], rstd=st[7],
                            dgamma=self.g(i, "mlp.ffn_ln.weight"))
@@ -338,7 +339,7 @@ class StudentEngine:
             ops.cast_transpose(t.g_2Hd, M, 2 * Hd, dst_t=t.g_T_2Hd)
             ops.cast_transpose(t.u2[i], M, D, dst_t=t.act_T_D)
             ops.gemm(t.g_T_2Hd, t.act_T_D, self._span(self.flat_grad, i, "mlp.w1.weight", 2 * Hd, D),
-                     M=2 * Hd, N=D, K=M)                                                          # dW1|dW2
+                     M=2 * Hd, N=D, K=M, k_splits=-1)                                             # dW1|dW2
             ops.col_reduce(t.g_2Hd, M, 2 * Hd, self._span(self.flat_grad, i, "mlp.w1.bias", 1, 2 * Hd).view(-1), ws)
             ops.gemm(t.g_2Hd, pk.w12T, t.g_D2, M=M)                                               # d_u2
             ops.col_reduce(t.g_D2, M, D, self.g(i, "norm2.bias"), ws, x=t.xmid[i], mean=st[4], rstd=st[5],
@@ -348,7 +349,7 @@ class StudentEngine:
             ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
             ops.col_reduce(dx, M, D, self.g(i, "attn.proj.bias"), ws)
             ops.cast_transpose(t.aln[i], M, D, dst_t=t.act_T_D)
-            ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.proj.weight"), M=D, N=D, K=M)            # dWproj
+            ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.proj.weight"), M=D, N=D, K=M, k_splits=-1)  # dWproj
             ops.gemm(t.g_bf_D, pk.wprojT, t.g_D2, M=M)                                            # d_aln
             ops.col_reduce(t.g_D2, M, D, self.g(i, "attn.inner_attn_ln.bias"), ws, x=t.att[i], mean=st[2], rstd=st[3],
                            dgamma=self.g(i, "attn.inner_attn_ln.weight"))
@@ -360,13 +361,13 @@ class StudentEngine:
                                   (fr.rope_cos, fr.rope_sin), t.delta, t.g_3D)                    # d_qkv (raw projections)
                 ops.cast_transpose(t.g_3D, M, 3 * D, dst_t=t.g_T_3D)
                 ops.gemm(t.g_T_3D, t.act_T_D, self._span(self.flat_grad, i, "attn.q_proj.weight", 3 * D, D),
-                         M=3 * D, N=D, K=M)                                                       # dWq|dWk|dWv
+                         M=3 * D, N=D, K=M, k_splits=-1)                                          # dWq|dWk|dWv
                 ops.col_reduce(t.g_3D, M, D, self.g(i, "attn.q_bias"), ws, lddy=3 * D)
                 ops.col_reduce(t.g_3D[:, 2 * D:], M, D, self.g(i, "attn.v_bias"), ws, lddy=3 * D)
                 ops.gemm(t.g_3D, pk.wqkvT, t.g_D2, M=M)                                           # d_u
             else:
                 ops.cast_transpose(d_att, M, D, dst_t=t.g_T_D)
-                ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.v_proj.weight"), M=D, N=D, K=M)
+                ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.v_proj.weight"), M=D, N=D, K=M, k_splits=-1)
                 ops.col_reduce(d_att, M, D, self.g(i, "attn.v_bias"), ws)
                 ops.gemm(d_att, pk.wvT, t.g_D2, M=M)
             ops.col_reduce(t.g_D2, M, D, self.g(i, "norm1.bias"), ws, x=t.x[i], mean=st[0], rstd=st[1],

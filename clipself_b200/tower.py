@@ -17,6 +17,7 @@ All arithmetic runs in the CUDA library (clipself_b200/csrc); torch only owns th
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -80,7 +81,9 @@ def rope_vectors(grid: int, head_dim: int, pt_seq_len: int, theta: float = 10000
 
 class PackedBlock:
     __slots__ = ("wqkv", "bqkv", "wv", "bv", "wproj", "bproj", "w12", "b12", "w3", "b3",
-                 "g1", "b1", "gi", "bi", "g2", "b2", "gf", "bf")
+                 "g1", "b1", "gi", "bi", "g2", "b2", "gf", "bf",
+                 # LayerNorm-folded operands (frozen weights): W*diag(gamma), rowsum(W'), W*beta + b
+                 "wproj_f", "c1_proj", "c2_proj", "w3_f", "c1_w3", "c2_w3")
 
 
 class PackedTower:
@@ -135,6 +138,16 @@ class PackedTower:
             pb.gi, pb.bi = f(p + "attn.inner_attn_ln.weight"), f(p + "attn.inner_attn_ln.bias")
             pb.g2, pb.b2 = f(p + "norm2.weight"), f(p + "norm2.bias")
             pb.gf, pb.bf = f(p + "mlp.ffn_ln.weight"), f(p + "mlp.ffn_ln.bias")
+            # One-time weight preprocessing for the folded inner_attn_ln / ffn_ln (see cs_gemm_epilogue_t):
+            #   proj(LN(a)) = rstd * (a @ W'^T - mean * c1) + c2,  W' = W diag(gamma), c1 = rowsum(W'), c2 = W beta + b.
+            # c1 is summed from the bf16-rounded W' so it matches what the tensor cores multiply.
+            wp, w3 = f(p + "attn.proj.weight"), f(p + "mlp.w3.weight")
+            pb.wproj_f = ops.cast_pad_bf16(wp * pb.gi[None, :])
+            pb.c1_proj = pb.wproj_f.float().sum(1).contiguous()
+            pb.c2_proj = (wp @ pb.bi + pb.bproj).contiguous()
+            pb.w3_f = ops.cast_pad_bf16(w3 * pb.gf[None, :])
+            pb.c1_w3 = pb.w3_f.float().sum(1).contiguous()
+            pb.c2_w3 = (w3 @ pb.bf + pb.b3).contiguous()
 
 
 class Workspace:
@@ -150,13 +163,14 @@ class Workspace:
         self.att = torch.empty(rows, D, **bf)
         self.h = torch.empty(rows, Hd, **bf)
         self.h2 = torch.empty(rows, Hd, **bf)
+        self.stats_att = torch.empty(rows, 2 * cfg.heads, 2, device=device, dtype=torch.float32)
+        self.stats_h = torch.empty(rows, max(Hd // 128, 1), 2, device=device, dtype=torch.float32)
 
 
 class TowerEngine:
     """Runs the kernel sequence of one tower."""
 
     def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device, chunk_images: Optional[int] = None):
-        import os
         L.require_device()
         if chunk_images is None:
             chunk_images = int(os.environ.get("CLIPSELF_TEACHER_CHUNK", "256"))
@@ -166,6 +180,10 @@ class TowerEngine:
         self.chunk_images = chunk_images
         self._ws: Optional[Workspace] = None
         self.scale = cfg.head_dim ** -0.5
+        # LayerNorm folding needs the producers' row statistics: the tcgen05 attention kernel (N <= 224)
+        # and an even number of SwiGLU tiles per row
+        self.fold_proj = cfg.tokens <= 224 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+        self.fold_w3 = (cfg.hidden // 128) % 2 == 0 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
 
     # ------------------------------------------------------------------ helpers
     def workspace(self, images: int) -> Workspace:
@@ -190,18 +208,28 @@ class TowerEngine:
         M = B * N
         x, u = ws.x, ws.u
         ops.layernorm_fwd(x, M, D, pb.g1, pb.b1, cfg.ln_eps, u)
+        fold_proj = with_attention and self.fold_proj
         if with_attention:
             ops.gemm(u, pb.wqkv, ws.qkv, M=M, mode=L.EPI_QKV_ROPE, bias=pb.bqkv, rope=(self.w.rope_pos, self.w.rope_freq),
                      tokens=N, rope_cols=2 * D)
-            ops.attention_fwd(ws.qkv, B, N, cfg.heads, self.scale, ws.att)
+            ops.attention_fwd(ws.qkv, B, N, cfg.heads, self.scale, ws.att, row_stats=ws.stats_att if fold_proj else None)
         else:
             ops.gemm(u, pb.wv, ws.att, M=M, bias=pb.bv)
-        ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, cfg.ln_eps, u)
-        ops.gemm(u, pb.wproj, x, M=M, bias=pb.bproj, residual=x)
+        if fold_proj:      # inner_attn_ln folded into the proj GEMM's epilogue
+            ops.gemm(ws.att, pb.wproj_f, x, M=M, bias=pb.c2_proj, residual=x,
+                     ln_fold=(ws.stats_att, pb.c1_proj, 2 * cfg.heads, D, cfg.ln_eps))
+        else:
+            ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, cfg.ln_eps, u)
+            ops.gemm(u, pb.wproj, x, M=M, bias=pb.bproj, residual=x)
         ops.layernorm_fwd(x, M, D, pb.g2, pb.b2, cfg.ln_eps, u)
-        ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12)
-        ops.layernorm_fwd(ws.h, M, cfg.hidden, pb.gf, pb.bf, cfg.ln_eps, ws.h2)
-        ops.gemm(ws.h2, pb.w3, x, M=M, bias=pb.b3, residual=x)
+        if self.fold_w3:   # ffn_ln folded into the w3 GEMM's epilogue
+            ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12, stats_out=ws.stats_h)
+            ops.gemm(ws.h, pb.w3_f, x, M=M, bias=pb.c2_w3, residual=x,
+                     ln_fold=(ws.stats_h, pb.c1_w3, cfg.hidden // 128, cfg.hidden, cfg.ln_eps))
+        else:
+            ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12)
+            ops.layernorm_fwd(ws.h, M, cfg.hidden, pb.gf, pb.bf, cfg.ln_eps, ws.h2)
+            ops.gemm(ws.h2, pb.w3, x, M=M, bias=pb.b3, residual=x)
 
     # ------------------------------------------------------------------ teacher
     def forward_cls(self, images: Tensor, out: Optional[Tensor] = None, ready_events=None) -> Tensor:

@@ -144,6 +144,21 @@ typedef struct {
     const float* pos_embed;  /* [tokens, N] f32 (TOKENS) */
     float alpha;             /* scale applied to acc before everything else (1.0 default) */
     int32_t reserved;        /* must be 0 (debug ablation switches) */
+    /* LayerNorm folding (frozen teacher): the GEMM runs on the UN-normalised rows a with weights
+     * W' = W*diag(gamma); the epilogue applies  y = rstd*(acc - mean*ln_c1[n]) + bias[n]  with
+     * ln_c1 = rowsum(W'), bias = W*beta + b, and (mean, rstd) of each input row rebuilt from
+     * ln_parts partial (sum, sumsq) pairs:  ln_stats [M, ln_parts, 2].  STORE / f32 / in-place
+     * residual only.  NULL ln_stats disables it. */
+    const float* ln_stats;
+    const float* ln_c1;      /* [N] */
+    int32_t ln_parts;
+    int32_t ln_dim;          /* number of elements the statistics run over (K of the GEMM) */
+    float ln_eps;
+    int32_t reserved2;       /* split-K: 0 = off, -1 = choose, n = n splits; partial products are red.add'ed into
+                              * `out`, which must be zero on entry (f32 STORE, no residual) */
+    /* SWIGLU only, optional: per (row, 256-wide tile) partial (sum, sumsq) of the bf16 outputs:
+     * stats_out [M, N/256, 2] — the ln_stats of the following w3 GEMM (ffn_ln folded). */
+    float* stats_out;
 } cs_gemm_epilogue_t;
 
 /* C[M,N] = A[M,K] · W[N,K]^T on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM ->
@@ -163,9 +178,13 @@ int cs_pack_swiglu_weights(const void* w1, const void* w2, cs_dtype_t dtype, int
 
 /* Non-causal softmax attention over the packed projections (eva_vit_model.py:206-217 / 221-246):
  *   qkv [B*N, 3*D] bf16 (q | k | v, each H heads of 64, RoPE already applied to q,k),
- *   out [B*N, D] bf16;  lse [B,H,N] f32 optional (needed for the backward).  head_dim must be 64. */
+ *   out [B*N, D] bf16;  lse [B,H,N] f32 optional (needed for the backward).  head_dim must be 64.
+ *   row_stats (optional, N <= 224 only): [B*N, 2H, 2] f32 partial (sum, sum of squares) of every
+ *   output row per (head, 32-dim half) — consumed by the LayerNorm-folded proj GEMM (ln_* fields of
+ *   cs_gemm_epilogue_t) so inner_attn_ln (eva_vit_model.py:218) needs no pass of its own.
+ *   N <= 224 runs the tcgen05 kernel (S/O in TMEM), longer sequences the streaming kernel. */
 int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
-                     float* lse, void* stream);
+                     float* lse, float* row_stats, void* stream);
 
 /* f32 -> bf16 cast of a [rows, cols] matrix into a (possibly wider, zero padded) bf16 matrix. */
 int cs_cast_pad_bf16(const float* src, int64_t rows, int64_t cols, int64_t lds, void* dst_bf16,

@@ -134,3 +134,53 @@ def test_gemm_tokens(dev):
     ref[:, 1:] = (a.float() @ w.float().t() + bias).view(B, tokens - 1, D) + pos[1:]
     ok, msg = _report("tokens", x, ref.view(B * tokens, D), 2e-3)
     assert ok, msg
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(768, 2048, 12608, -1), (2304, 768, 12608, 3), (256, 128, 1000, 2), (768, 768, 12608, -1)])
+def test_gemm_split_k(dev, M, N, K, splits):
+    from clipself_b200 import ops
+    a, w = _mk(M, N, K, dev, lda=(K + 7) // 8 * 8, seed=7)
+    out = torch.zeros(M, N, device=dev)
+    ops.gemm(a, w, out, M=M, N=N, K=K, k_splits=splits)
+    ref = a[:, :K].float() @ w[:, :K].float().t()
+    ok, msg = _report(f"split-K {M}x{N}x{K} splits={splits}", out, ref, 2e-3)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("M,N,K,parts", [(1000, 768, 2048, 16), (3000, 768, 768, 24), (300, 128, 128, 4)])
+def test_gemm_ln_fold(dev, M, N, K, parts):
+    """y = x + LN(a) W^T + b computed as rstd*(a W'^T - mean*c1) + c2 from partial row statistics."""
+    from clipself_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    a = (torch.randn(M, K, generator=g) * 1.7 + 0.4).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    gamma = (1 + 0.2 * torch.randn(K, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(K, generator=g)).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    x = torch.randn(M, N, generator=g).to(dev)
+    ref = x + torch.nn.functional.layer_norm(a.float(), (K,), gamma, beta, 1e-6) @ W.to(torch.bfloat16).float().t() + b
+    wf = ops.cast_pad_bf16(W * gamma[None, :])
+    c1 = wf.float().sum(1).contiguous()
+    c2 = (W @ beta + b).contiguous()
+    af = a.float().view(M, parts, K // parts)
+    stats = torch.stack([af.sum(-1), (af * af).sum(-1)], dim=-1).contiguous()          # [M, parts, 2]
+    ops.gemm(a, wf, x, bias=c2, residual=x, ln_fold=(stats, c1, parts, K, 1e-6))
+    ok, msg = _report(f"ln-fold {M}x{N}x{K}", x, ref, 1.5e-2)
+    assert ok, msg
+
+
+def test_gemm_swiglu_stats(dev):
+    from clipself_b200 import ops, _lib as L
+    D, Hd, M = 768, 2048, 700
+    g = torch.Generator().manual_seed(9)
+    w1 = (torch.randn(Hd, D, generator=g) / D ** 0.5).to(dev)
+    w2 = (torch.randn(Hd, D, generator=g) / D ** 0.5).to(dev)
+    b1, b2 = torch.randn(Hd, generator=g).to(dev), torch.randn(Hd, generator=g).to(dev)
+    a = torch.randn(M, D, generator=g).to(torch.bfloat16).to(dev)
+    packed, b12 = ops.pack_swiglu_weights(w1, w2, b1, b2, D)
+    out = torch.empty(M, Hd, device=dev, dtype=torch.bfloat16)
+    stats = torch.full((M, Hd // 128, 2), float("nan"), device=dev)
+    ops.gemm(a, packed, out, mode=L.EPI_SWIGLU, bias=b12, stats_out=stats)
+    o = out.float().view(M, Hd // 128, 128)
+    torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-4, atol=1e-3)

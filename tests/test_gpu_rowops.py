@@ -72,3 +72,11 @@ def test_attention_fwd(dev, B, N, H):
     print(f"attention B={B} N={N} H={H}: max err {err:.4e}")
     assert err < 2e-2
     torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=1e-3)
+    if N <= 224:
+        stats = torch.full((B * N, 2 * H, 2), float("nan"), device=dev)
+        out2 = torch.empty_like(out)
+        ops.attention_fwd(qkv, B, N, H, 0.125, out2, None, stats)
+        assert torch.equal(out2, out)
+        o = out.float().view(B * N, 2 * H, 32)
+        torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-4, atol=1e-4)
