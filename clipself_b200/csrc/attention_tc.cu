@@ -180,14 +180,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
         float* xmax = xch;                                         // [2][128]
         float* xsum = xch + 256;                                   // [2][128]
-        for (int tt = 0; tt < total_tiles; ++tt) {
-            const int il = tt / p.ntm, mt = tt % p.ntm;
-            const int item = blockIdx.x + il * gridDim.x;
-            const int b = item / p.H, h = item % p.H;
+        // row max of one tile (this thread's share of the key columns, then exchanged with the partner warp)
+        auto row_max = [&](int tt) -> float {
             mbar_wait(s_full(tt & 1), (uint32_t)(tt >> 1) & 1u);
             tc_fence_after();
             const uint32_t ts = tmem_base + lane_addr + (uint32_t)((tt & 1) * S_STRIDE);
-            // pass 1: row max over this thread's share of the valid keys
             float mx = -INFINITY;
             for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[32];
@@ -199,7 +196,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             }
             xmax[half * 128 + r] = mx;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            mx = fmaxf(xmax[r], xmax[128 + r]);
+            return fmaxf(xmax[r], xmax[128 + r]);
+        };
+        float mx = total_tiles > 0 ? row_max(0) : 0.f;
+        for (int tt = 0; tt < total_tiles; ++tt) {
+            const int il = tt / p.ntm, mt = tt % p.ntm;
+            const int item = blockIdx.x + il * gridDim.x;
+            const int b = item / p.H, h = item % p.H;
+            const uint32_t ts = tmem_base + lane_addr + (uint32_t)((tt & 1) * S_STRIDE);
             const float mxs = mx * p.scale_log2;
             // P buffer must have been consumed by the previous tile's PV
             mbar_wait(p_empty, ((uint32_t)tt & 1u) ^ 1u);
@@ -231,6 +235,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             tc_fence_before();
             mbar_arrive(p_full);
             mbar_arrive(s_empty(tt & 1));
+            // the next tile's S is already in TMEM: take its row max while the tensor core runs P V
+            const float mx_this = mx;
+            if (tt + 1 < total_tiles) mx = row_max(tt + 1);
             // epilogue: O / sum; this warp converts 32 of the 64 output dims
             mbar_wait(o_full, (uint32_t)tt & 1u);
             tc_fence_after();
@@ -255,19 +262,18 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                     pk.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
                     *reinterpret_cast<uint4*>(dst + 8 * i) = pk;
                     if (p.row_stats != nullptr) {
-                        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-                        for (int z = 0; z < 4; ++z) {
-                            const float2 f = unpack_bf16(w4[z]);   // statistics of the values as stored
-                            s1 += f.x + f.y;
-                            s2 += f.x * f.x + f.y * f.y;
+                        for (int z = 0; z < 8; ++z) {          // statistics for the folded inner_attn_ln (pre-rounding values)
+                            const float f = __uint_as_float(o[8 * i + z]) * inv;
+                            s1 += f;
+                            s2 += f * f;
                         }
                     }
                 }
                 if (p.row_stats != nullptr)
                     *reinterpret_cast<float2*>(p.row_stats + (((long long)b * p.N + row) * (2 * p.H) + 2 * h + half) * 2) = make_float2(s1, s2);
                 if (p.lse != nullptr && half == 0)
-                    p.lse[((long long)b * p.H + h) * p.N + row] = mx * p.scale + logf(sum);
+                    p.lse[((long long)b * p.H + h) * p.N + row] = mx_this * p.scale + logf(sum);
             }
             // xmax / xsum are rewritten by the next tile only after its bar.sync / p_full round
             asm volatile("bar.sync 2, 256;" ::: "memory");

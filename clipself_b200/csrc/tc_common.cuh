@@ -38,7 +38,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (clock64() - t0 > (threadIdx.x >= 64 ? 2000000000ll : 4000000000ll)) {   // consumers report first
+            printf("clipself_b200: mbarrier wait timed out (smem 0x%x parity %u block %d thread %d)\n", bar, parity,
+                   (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,

@@ -182,5 +182,6 @@ def test_gemm_swiglu_stats(dev):
     stats = torch.full((M, Hd // 128, 2), float("nan"), device=dev)
     ops.gemm(a, packed, out, mode=L.EPI_SWIGLU, bias=b12, stats_out=stats)
     o = out.float().view(M, Hd // 128, 128)
-    torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-4, atol=1e-3)
-    torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-4, atol=1e-3)
+    # statistics are taken before the bf16 rounding of the stored values
+    torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=5e-3, atol=0.15)
+    torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=5e-3, atol=0.5)

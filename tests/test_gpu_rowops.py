@@ -78,5 +78,5 @@ def test_attention_fwd(dev, B, N, H):
         ops.attention_fwd(qkv, B, N, H, 0.125, out2, None, stats)
         assert torch.equal(out2, out)
         o = out.float().view(B * N, 2 * H, 32)
-        torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-4, atol=1e-4)
-        torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=5e-3, atol=1e-2)      # taken before bf16 rounding
+        torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=5e-3, atol=1e-2)
