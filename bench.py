@@ -128,6 +128,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if distributed:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"              # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=device)
     _lib.require_device()
     wl = WORKLOADS[args.workload]
@@ -216,6 +218,12 @@ def run_b200(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # per launch, from the committed ncu capture
+    except (OSError, KeyError):
+        pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
     ms_step = ms_total / args.steps
@@ -238,7 +246,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "cs::gemm::gemm_kernel (tcgen05)", "achieved": round(achieved, 1),
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": len(prof),
                      "gemm_share_of_step": round(gemm_ms / ms_step, 3)},
         "cpu_baseline": cpu_baseline(cfg_name=wl["model"], budget_s=25.0),

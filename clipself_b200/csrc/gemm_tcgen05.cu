@@ -36,7 +36,7 @@ struct Cfg {
     static constexpr int EPI_ROWSTAT_BYTES = 256;            // (mean, rstd) of this warp's 32 rows (LN folding)
     static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + 2 * EPI_BIAS_BYTES + EPI_ROWSTAT_BYTES;  // bias + ln_c1
     static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-    static constexpr int ROPE_BYTES = 512;                   // 64 grid positions + 16 frequencies (+pad)
+    static constexpr int ROPE_BYTES = 2 * 16 * 64 * 4;       // cos / sin of pos[g] * freq[q]: [2][16 freqs][64 grid positions]
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + ROPE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
 };
 
@@ -159,11 +159,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                         const int n = n0 + c;
                         if (n < ep.rope_cols && rot) {
                             // head-dim offset 0..31 rotates by the token's grid ROW, 32..63 by its COLUMN
-                            const float pos = srope[(n & 32) ? gj : gi];
+                            const int g = (n & 32) ? gj : gi;
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
-                                float sn, cs_;
-                                __sincosf(pos * srope[64 + q], &sn, &cs_);
+                                const float cs_ = srope[q * 64 + g], sn = srope[1024 + q * 64 + g];
                                 const float x0 = v[2 * q], x1 = v[2 * q + 1];
                                 v[2 * q] = x0 * cs_ - x1 * sn;
                                 v[2 * q + 1] = x1 * cs_ + x0 * sn;
@@ -332,9 +331,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if constexpr (MODE == CS_EPI_QKV_ROPE) {
-        if (threadIdx.x >= 64 && threadIdx.x < 64 + 80) {
-            const int i = threadIdx.x - 64;
-            srope[i] = i < 64 ? (i < ep.rope_grid ? ep.rope_pos[i] : 0.f) : ep.rope_freq[i - 64];
+        // rotary table of this launch: angle(g, q) = pos[g] * freq[q] (f32 product as in rope.py:129), accurate
+        // sincosf once per CTA; layout [q][g] so that lanes with different grid positions hit different banks
+        for (int i = threadIdx.x; i < 16 * 64; i += NUM_THREADS) {
+            const int q = i >> 6, g = i & 63;
+            float sn = 0.f, cs_ = 1.f;
+            if (g < ep.rope_grid) sincosf(ep.rope_pos[g] * ep.rope_freq[q], &sn, &cs_);
+            srope[i] = cs_;
+            srope[1024 + i] = sn;
         }
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);

@@ -28,8 +28,9 @@ namespace rowops {
 
 constexpr int LN_WARPS = 8;
 
-// One warp per row.  The row is staged in shared memory (single HBM read), statistics are the
-// two-pass mean / centred variance in f32 (same numerics as ATen's layer_norm).
+// One warp per row, any D.  The row is staged in shared memory (single HBM read), statistics are the
+// two-pass mean / centred variance in f32 (same numerics as ATen's layer_norm).  Used for the widths
+// without a register-resident instantiation (e.g. ViT-L's 2730-wide ffn_ln).
 template <typename TIn>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const TIn* __restrict__ x, long long ldx, long long M, int D, int row_div, int row_mul,
@@ -44,53 +45,27 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, long long ldx, long long M, int 
     const TIn* xr = x + prow * ldx;
     float* s = s_rows + warp * D;
     float sum = 0.f;
-    if constexpr (sizeof(TIn) == 4) {
-        for (int i = lane * 4; i < D; i += 128) {
-            const float4 v = *reinterpret_cast<const float4*>(xr + i);
-            *reinterpret_cast<float4*>(s + i) = v;
-            sum += (v.x + v.y) + (v.z + v.w);
-        }
-    } else {
-        for (int i = lane * 8; i < D; i += 256) {
-            const uint4 u = *reinterpret_cast<const uint4*>(xr + i);
-            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-            *reinterpret_cast<float4*>(s + i) = make_float4(a.x, a.y, b.x, b.y);
-            *reinterpret_cast<float4*>(s + i + 4) = make_float4(c.x, c.y, d.x, d.y);
-            sum += ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
-        }
+    for (int i = lane; i < D; i += 32) {
+        const float v = (float)xr[i];
+        s[i] = v;
+        sum += v;
     }
     sum = warp_sum(sum);
     const float mean = sum / (float)D;
-    __syncwarp();
     float var = 0.f;
-    for (int i = lane * 4; i < D; i += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(s + i);
-        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-        var += (a * a + b * b) + (c * c + d * d);
+    for (int i = lane; i < D; i += 32) {
+        const float d = s[i] - mean;
+        var += d * d;
     }
     var = warp_sum(var);
     const float rstd = rsqrtf(var / (float)D + eps);
     __nv_bfloat16* yr = y + m * ldy;
-    for (int i = lane * 8; i < D; i += 256) {
-        const float4 v0 = *reinterpret_cast<const float4*>(s + i);
-        const float4 v1 = *reinterpret_cast<const float4*>(s + i + 4);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + i);
-        const float4 g1 = *reinterpret_cast<const float4*>(gamma + i + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(beta + i);
-        const float4 b1 = *reinterpret_cast<const float4*>(beta + i + 4);
-        uint4 o;
-        o.x = pack_bf16((v0.x - mean) * rstd * g0.x + b0.x, (v0.y - mean) * rstd * g0.y + b0.y);
-        o.y = pack_bf16((v0.z - mean) * rstd * g0.z + b0.z, (v0.w - mean) * rstd * g0.w + b0.w);
-        o.z = pack_bf16((v1.x - mean) * rstd * g1.x + b1.x, (v1.y - mean) * rstd * g1.y + b1.y);
-        o.w = pack_bf16((v1.z - mean) * rstd * g1.z + b1.z, (v1.w - mean) * rstd * g1.w + b1.w);
-        *reinterpret_cast<uint4*>(yr + i) = o;
-    }
+    for (int i = lane; i < D; i += 32) yr[i] = __float2bfloat16((s[i] - mean) * rstd * gamma[i] + beta[i]);
     if (lane == 0) {
         if (mean_out) mean_out[m] = mean;
         if (rstd_out) rstd_out[m] = rstd;
     }
 }
-
 
 // Register-resident variant for the row widths of the towers (D = 32 lanes x VPL 16-byte vectors):
 // every load of the row is in flight at once, statistics and normalisation never leave registers.
@@ -294,9 +269,10 @@ extern "C" int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, 
                                 int row_mul, int row_off, const float* gamma, const float* beta, float eps,
                                 void* y_bf16, int64_t ldy, float* mean, float* rstd, void* stream) {
     CS_CHECK_ARG(x && gamma && beta && y_bf16, "cs_layernorm_fwd: null pointer");
-    CS_CHECK_ARG(M > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && row_mul >= 1,
-                 "cs_layernorm_fwd: D, ldx, ldy must be multiples of 8 (D=%d ldx=%lld ldy=%lld)", D, (long long)ldx,
-                 (long long)ldy);
+    CS_CHECK_ARG(M > 0 && D > 0 && ldx >= D && ldy >= D && row_mul >= 1, "cs_layernorm_fwd: bad shape (D=%d ldx=%lld ldy=%lld)", D,
+                 (long long)ldx, (long long)ldy);
+    const bool vec_ok = ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y_bf16 % 16 == 0) &&
+                        ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     // register-resident fast paths for the widths of the EVA02 towers
 #define LN_REG(T, VPL)                                                                                          \
@@ -305,12 +281,12 @@ extern "C" int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, 
         CS_LAUNCH_CHECK();                                                                                      \
         return CS_OK;                                                                                           \
     }
-    if (x_dtype == CS_F32) {
+    if (vec_ok && x_dtype == CS_F32) {
         if (D == 768) LN_REG(float, 6)
         if (D == 1024) LN_REG(float, 8)
         if (D == 2048) LN_REG(float, 16)
         if (D == 128) LN_REG(float, 1)
-    } else {
+    } else if (vec_ok) {
         if (D == 768) LN_REG(__nv_bfloat16, 3)
         if (D == 1024) LN_REG(__nv_bfloat16, 4)
         if (D == 2048) LN_REG(__nv_bfloat16, 8)

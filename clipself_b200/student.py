@@ -161,7 +161,10 @@ class StudentEngine:
 
     def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device):
         L.require_device()
-        assert cfg.hidden % 128 == 0 and cfg.head_dim == 64
+        if cfg.hidden % 128 != 0:
+            raise NotImplementedError(f"training path with SwiGLU hidden {cfg.hidden} (ViT-L/14) needs the padded student "
+                                      "packs: inference / teacher are supported, training is next round (DESIGN.md §9)")
+        assert cfg.head_dim == 64
         self.cfg, self.device = cfg, device
         self.layout = FlatLayout(cfg)
         lay = self.layout

@@ -53,6 +53,12 @@ class TowerCfg:
     def head_dim(self) -> int:
         return self.width // self.heads
 
+    @property
+    def hidden_pad(self) -> int:
+        """SwiGLU hidden width padded to the 128-column packing unit (ViT-L: 2730 -> 2816); padded
+        columns carry exact zeros (zero weights / biases) and LayerNorm statistics use `hidden`."""
+        return (self.hidden + 127) // 128 * 128
+
 
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
@@ -93,7 +99,6 @@ class PackedTower:
     def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device):
         assert cfg.head_dim == 64, "kernels are specialised for head_dim 64 (all EVA02-CLIP configs)"
         assert cfg.width % 64 == 0 and cfg.embed_dim % 32 == 0
-        assert cfg.hidden % 128 == 0, "hidden must be a multiple of 128 (ViT-L 2730 padding: DESIGN.md roadmap)"
         self.cfg = cfg
         self.device = device
         cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
@@ -132,7 +137,7 @@ class PackedTower:
             pb.bproj = f(p + "attn.proj.bias")
             pb.w12, pb.b12 = ops.pack_swiglu_weights(f(p + "mlp.w1.weight"), f(p + "mlp.w2.weight"),
                                                      f(p + "mlp.w1.bias"), f(p + "mlp.w2.bias"), D)
-            pb.w3 = ops.cast_pad_bf16(f(p + "mlp.w3.weight"))
+            pb.w3 = ops.cast_pad_bf16(f(p + "mlp.w3.weight"), cfg.hidden_pad)
             pb.b3 = f(p + "mlp.w3.bias")
             pb.g1, pb.b1 = f(p + "norm1.weight"), f(p + "norm1.bias")
             pb.gi, pb.bi = f(p + "attn.inner_attn_ln.weight"), f(p + "attn.inner_attn_ln.bias")
@@ -145,7 +150,7 @@ class PackedTower:
             pb.wproj_f = ops.cast_pad_bf16(wp * pb.gi[None, :])
             pb.c1_proj = pb.wproj_f.float().sum(1).contiguous()
             pb.c2_proj = (wp @ pb.bi + pb.bproj).contiguous()
-            pb.w3_f = ops.cast_pad_bf16(w3 * pb.gf[None, :])
+            pb.w3_f = ops.cast_pad_bf16(w3 * pb.gf[None, :], cfg.hidden_pad)
             pb.c1_w3 = pb.w3_f.float().sum(1).contiguous()
             pb.c2_w3 = (w3 @ pb.bf + pb.b3).contiguous()
 
@@ -154,7 +159,7 @@ class Workspace:
     """Activation scratch for one forward-only chunk of `rows` token rows."""
 
     def __init__(self, cfg: TowerCfg, rows: int, device):
-        D, Hd = cfg.width, cfg.hidden
+        D, Hd = cfg.width, cfg.hidden_pad
         bf = dict(device=device, dtype=torch.bfloat16)
         self.rows = rows
         self.x = torch.empty(rows, D, device=device, dtype=torch.float32)
@@ -162,7 +167,7 @@ class Workspace:
         self.qkv = torch.empty(rows, 3 * D, **bf)
         self.att = torch.empty(rows, D, **bf)
         self.h = torch.empty(rows, Hd, **bf)
-        self.h2 = torch.empty(rows, Hd, **bf)
+        self.h2 = torch.zeros(rows, Hd, **bf)           # padded columns must stay finite (they meet zero weights)
         self.stats_att = torch.empty(rows, 2 * cfg.heads, 2, device=device, dtype=torch.float32)
         self.stats_h = torch.empty(rows, max(Hd // 128, 1), 2, device=device, dtype=torch.float32)
 
@@ -183,7 +188,7 @@ class TowerEngine:
         # LayerNorm folding needs the producers' row statistics: the tcgen05 attention kernel (N <= 224)
         # and an even number of SwiGLU tiles per row
         self.fold_proj = cfg.tokens <= 224 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
-        self.fold_w3 = (cfg.hidden // 128) % 2 == 0 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+        self.fold_w3 = (cfg.hidden_pad // 128) % 2 == 0 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
 
     # ------------------------------------------------------------------ helpers
     def workspace(self, images: int) -> Workspace:
@@ -225,7 +230,7 @@ class TowerEngine:
         if self.fold_w3:   # ffn_ln folded into the w3 GEMM's epilogue
             ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12, stats_out=ws.stats_h)
             ops.gemm(ws.h, pb.w3_f, x, M=M, bias=pb.c2_w3, residual=x,
-                     ln_fold=(ws.stats_h, pb.c1_w3, cfg.hidden // 128, cfg.hidden, cfg.ln_eps))
+                     ln_fold=(ws.stats_h, pb.c1_w3, cfg.hidden_pad // 128, cfg.hidden, cfg.ln_eps))
         else:
             ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12)
             ops.layernorm_fwd(ws.h, M, cfg.hidden, pb.gf, pb.bf, cfg.ln_eps, ws.h2)

@@ -54,7 +54,8 @@ def build_reference_model(cfg: O.TowerCfg, seed: int, name: str | None):
     return model
 
 
-def run_case(tag, cfg, name, batch, K, kind, ragged, seed, store_inputs, store_all_grads, tap_blocks=None):
+def run_case(tag, cfg, name, batch, K, kind, ragged, seed, store_inputs, store_all_grads, tap_blocks=None,
+             backward=True):
     student = build_reference_model(cfg, seed, name)
     teacher = build_reference_model(cfg, seed + 1, name)
     student.lock_image_tower(unlocked_groups=cfg.layers)      # main.py:161-166
@@ -75,7 +76,8 @@ def run_case(tag, cfg, name, batch, K, kind, ragged, seed, store_inputs, store_a
     for h in hooks:
         h.remove()
     loss = losses["loss_cosine"]
-    loss.backward()
+    if backward:
+        loss.backward()
 
     out = dict(seed=np.int64(seed), loss=loss.detach().numpy(),
                logit_scale_exp=logit_scale.detach().numpy(), batch_size=np.int64(bs),
@@ -114,7 +116,7 @@ def run_case(tag, cfg, name, batch, K, kind, ragged, seed, store_inputs, store_a
         out["images_checksum"] = np.float64(images.double().sum().item())
         out["crops_checksum"] = np.float64(crops.double().sum().item())
     names, norms, sums = [], [], []
-    for k, p in student.visual.named_parameters():
+    for k, p in (student.visual.named_parameters() if backward else []):
         if "rope" in k:
             continue
         has = p.grad is not None
@@ -140,3 +142,6 @@ if __name__ == "__main__":
     # BASELINE.json configs[0]: ViT-B/16, 2x224x224, 8 patch-boxes/img
     run_case("cfg1_b16", O.CFG_B16, "EVA02-CLIP-B-16", batch=2, K=8, kind="grid", ragged=False, seed=300,
              store_inputs=False, store_all_grads=False, tap_blocks=(0, 10))
+    # BASELINE.json configs[3]/[4] architecture (EVA02 ViT-L/14 @336), forward only, 1 image x 2 boxes
+    run_case("l14_fwd", O.CFG_L14_336, "EVA02-CLIP-L-14-336", batch=1, K=2, kind="proposal", ragged=False, seed=400,
+             store_inputs=False, store_all_grads=False, tap_blocks=(0,), backward=False)

@@ -20,10 +20,10 @@ def _rel(a, b):
 
 
 CASES = {"tiny_ragged": (O.CFG_TINY, 3, 5, "proposal", True), "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
-         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False)}
+         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False), "l14_fwd": (O.CFG_L14_336, 1, 2, "proposal", False)}
 
 
-@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_grid", "cfg1_b16"])
+@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_grid", "cfg1_b16", "l14_fwd"])
 def test_tower_forward_vs_golden(golden, tag):
     """bf16 tensor-core path vs the reference's fp32 outputs.  Tolerance: rel-L2 <= 1.5e-2 on
     feature maps (the reference's own bf16-autocast deviation is stored in the fixture as the

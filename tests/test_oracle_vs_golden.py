@@ -11,6 +11,7 @@ CASES = {
     "tiny_ragged": (O.CFG_TINY, 3, 5, "proposal", True),
     "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
     "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False),
+    "l14_fwd": (O.CFG_L14_336, 1, 2, "proposal", False),
 }
 
 
@@ -111,3 +112,11 @@ def test_roi_align_matches_torchvision():
     ours = O.roi_align_1x1_nhwc(f, boxes)
     ref = tv.ops.roi_align(f.permute(0, 3, 1, 2).contiguous(), boxes, (1, 1), 1.0, -1, True)[..., 0, 0]
     np.testing.assert_allclose(ours.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_forward_l14_336(golden):
+    """EVA02 ViT-L/14 @336 (BASELINE.json configs[3]/[4] architecture): hidden 2730, patch 14, 577 tokens."""
+    g, out, _ = _run(golden, "l14_fwd", need_grad=False)
+    np.testing.assert_allclose(out["teacher"].numpy(), g["teacher"], rtol=5e-4, atol=1e-4)
+    np.testing.assert_allclose(out["dense"].numpy(), g["dense_nhwc"], rtol=5e-4, atol=1e-5)
+    np.testing.assert_allclose(out["loss"].item(), float(g["loss"]), rtol=2e-5)

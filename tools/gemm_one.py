@@ -6,7 +6,7 @@ from clipself_b200 import ops, _lib as L
 from clipself_b200.tower import rope_tables, rope_vectors
 which = sys.argv[1]
 dev = torch.device("cuda")
-M = 128 * 197
+M = 256 * 197
 cfgs = {"store": (4096, 768, L.EPI_STORE, torch.bfloat16, False), "proj": (768, 768, L.EPI_STORE, torch.float32, True),
         "swiglu": (4096, 768, L.EPI_SWIGLU, torch.bfloat16, False), "qkv": (2304, 768, L.EPI_QKV_ROPE, torch.bfloat16, False)}
 N, K, mode, odt, res = cfgs[which]
