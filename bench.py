@@ -36,6 +36,8 @@ WORKLOADS = {
     "cfg2": dict(model="EVA02-CLIP-B-16", batch=64, boxes=32, kind="grid"),
     # configs[2] (8-GPU variant of the same per-GPU shape, region-proposal boxes)
     "cfg3": dict(model="EVA02-CLIP-B-16", batch=64, boxes=32, kind="proposal"),
+    # configs[3]: EVA ViT-L/14 336^2, 16 images per GPU (global 128 on 8 GPUs), 32 boxes/img
+    "cfg4": dict(model="EVA02-CLIP-L-14-336", batch=16, boxes=32, kind="grid"),
     # small variants for smoke / debugging
     "mini": dict(model="EVA02-CLIP-B-16", batch=8, boxes=8, kind="grid"),
 }
@@ -233,7 +235,7 @@ def run_b200(args):
     step_tflops = value * flops_per_image(cfg, K) / 1e12
     h2d = sum(t.numel() * t.element_size() for t in host_batch)
     out = {
-        "metric": "images/sec (32 boxes/img) ViT-B/16@224 distill step", "value": round(value, 2), "unit": "images/sec",
+        "metric": f"images/sec ({K} boxes/img) {'ViT-B/16@224' if cfg.width == 768 else 'ViT-L/14@336'} distill step", "value": round(value, 2), "unit": "images/sec",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['model']} {cfg.image_size}px student+teacher, per-GPU batch {B}, "

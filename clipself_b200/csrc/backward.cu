@@ -120,10 +120,11 @@ __global__ void col_reduce_kernel(const float* __restrict__ partial, int S, int 
 // SwiGLU on the packed layout of cs_pack_swiglu_weights: hidden column j = t*128 + jj has its gate
 // at packed column t*256 + jj and its up value at t*256 + 128 + jj.
 // --------------------------------------------------------------------------------------------
+// split: 0 = packed (gate|up interleaved by 128), 1 = up columns start at Hd, >= 2 = up columns start at `split`
 __device__ __forceinline__ void swiglu_cols(int j, int Hd, int split, int& gate_col, int& up_col) {
     if (split) {
         gate_col = j;
-        up_col = Hd + j;
+        up_col = (split == 1 ? Hd : split) + j;
     } else {
         gate_col = (j >> 7) * 256 + (j & 127);
         up_col = gate_col + 128;
@@ -268,7 +269,7 @@ extern "C" int cs_col_reduce(const void* dy, cs_dtype_t dy_dtype, int64_t lddy, 
 extern "C" int cs_swiglu_fwd(const void* x12_bf16, int64_t M, int Hd, int64_t ld12, void* h_bf16, int64_t ldh,
                              int split_layout, void* stream) {
     CS_CHECK_ARG(x12_bf16 && h_bf16 && M > 0 && Hd > 0 && Hd % 2 == 0 && ld12 >= 2 * Hd && ldh >= Hd &&
-                     (split_layout || Hd % 128 == 0),
+                     (split_layout || Hd % 128 == 0) && (split_layout < 2 || (split_layout >= Hd && split_layout % 2 == 0 && ld12 >= split_layout + Hd)),
                  "cs_swiglu_fwd: bad argument (packed layout needs Hd %% 128 == 0)");
     const long long total = M * (Hd / 2);
     const int grid = (int)(((total + 255) / 256) < (long long)num_sms() * 16 ? ((total + 255) / 256) : (long long)num_sms() * 16);
@@ -281,7 +282,7 @@ extern "C" int cs_swiglu_fwd(const void* x12_bf16, int64_t M, int Hd, int64_t ld
 extern "C" int cs_swiglu_bwd(const void* x12_bf16, const void* dh_bf16, int64_t M, int Hd, int64_t ld12,
                              int64_t lddh, void* dx12_bf16, int split_layout, void* stream) {
     CS_CHECK_ARG(x12_bf16 && dh_bf16 && dx12_bf16 && M > 0 && Hd > 0 && Hd % 2 == 0 && ld12 >= 2 * Hd && lddh >= Hd &&
-                     (split_layout || Hd % 128 == 0),
+                     (split_layout || Hd % 128 == 0) && (split_layout < 2 || (split_layout >= Hd && split_layout % 2 == 0 && ld12 >= split_layout + Hd)),
                  "cs_swiglu_bwd: bad argument");
     const long long total = M * (Hd / 2);
     const int grid = (int)(((total + 255) / 256) < (long long)num_sms() * 16 ? ((total + 255) / 256) : (long long)num_sms() * 16);

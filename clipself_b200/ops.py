@@ -232,11 +232,12 @@ def attention_bwd(qkv: Tensor, out: Tensor, d_out: Tensor, lse: Tensor, B: int, 
 
 
 def cast_transpose(src: Tensor, M: int, N: int, dst: Optional[Tensor] = None, dst_t: Optional[Tensor] = None,
-                   lds: Optional[int] = None) -> None:
-    """src [M,N] (f32|bf16) -> dst [M,*] bf16 and/or dst_t [N,*] bf16."""
+                   lds: Optional[int] = None, ldd: Optional[int] = None, ldt: Optional[int] = None) -> None:
+    """src [M,N] (f32|bf16) -> dst [M,*] bf16 and/or dst_t [N,*] bf16 (ldd / ldt override the leading
+    dimensions when dst / dst_t are column-sliced views of wider matrices)."""
     call("cs_cast_transpose_bf16", _p(src), _dt(src), M, N, lds if lds is not None else src.shape[-1],
-         _p(dst), dst.shape[-1] if dst is not None else 0, _p(dst_t), dst_t.shape[-1] if dst_t is not None else 0,
-         _stream())
+         _p(dst), (ldd if ldd is not None else dst.shape[-1]) if dst is not None else 0, _p(dst_t),
+         (ldt if ldt is not None else dst_t.shape[-1]) if dst_t is not None else 0, _stream())
 
 
 def layernorm_bwd_dx(dy: Tensor, x: Tensor, M: int, D: int, mean: Tensor, rstd: Tensor, gamma: Tensor, dx: Tensor,
@@ -256,12 +257,13 @@ def col_reduce(dy: Tensor, M: int, D: int, dbeta: Tensor, workspace: Tensor, x: 
          _p(mean), _p(rstd), _p(dgamma), _p(dbeta), _p(workspace), workspace.numel(), _stream())
 
 
-def swiglu_fwd(x12: Tensor, M: int, Hd: int, h: Tensor, split: bool = True) -> Tensor:
+def swiglu_fwd(x12: Tensor, M: int, Hd: int, h: Tensor, split=True) -> Tensor:
+    """split: False = packed128 layout, True = up columns at Hd, int >= 2 = up columns at that offset."""
     call("cs_swiglu_fwd", _p(x12), M, Hd, x12.shape[-1], _p(h), h.shape[-1], int(split), _stream())
     return h
 
 
-def swiglu_bwd(x12: Tensor, dh: Tensor, M: int, Hd: int, dx12: Tensor, split: bool = True) -> Tensor:
+def swiglu_bwd(x12: Tensor, dh: Tensor, M: int, Hd: int, dx12: Tensor, split=True) -> Tensor:
     call("cs_swiglu_bwd", _p(x12), _p(dh), M, Hd, x12.shape[-1], dh.shape[-1], _p(dx12), int(split), _stream())
     return dx12
 

@@ -62,6 +62,7 @@ class FlatLayout:
 
         def place(full: str, shape):
             nonlocal off
+            off = (off + 3) // 4 * 4                       # every view starts 16-byte aligned (ViT-L: 2730-wide vectors)
             self.offset[full] = off
             self.shape[full] = shape
             n = 1
@@ -76,6 +77,7 @@ class FlatLayout:
                     tail.append(full)
                 else:
                     place(full, block_param_shape(cfg, nm))
+        off = (off + 3) // 4 * 4
         self.n_decay = off                      # [0, n_decay): 2-D weights, weight-decay group
         for i in range(cfg.layers):
             for nm in V_NAMES:
@@ -84,6 +86,7 @@ class FlatLayout:
                     tail.append(full)
                 else:
                     place(full, block_param_shape(cfg, nm))
+        off = (off + 3) // 4 * 4
         self.n_grad = off                       # [n_decay, n_grad): vectors, no-decay group
         for full in tail:
             nm = full.split(".", 2)[2]
@@ -104,14 +107,14 @@ class FlatLayout:
 
 
 class _BlockPack:
-    __slots__ = ("wqkv", "wqkvT", "bqkv", "wv", "wvT", "wproj", "wprojT", "w12", "w12T", "w3", "w3T")
+    __slots__ = ("wqkv", "wqkvT", "bqkv", "wv", "wvT", "wproj", "wprojT", "w12", "w12T", "b12", "w3", "w3T")
 
 
 class _Tape:
     """Saved activations of one student forward (allocated once per batch size)."""
 
     def __init__(self, cfg: TowerCfg, B: int, dev):
-        D, Hd, N, H, Lr = cfg.width, cfg.hidden, cfg.tokens, cfg.heads, cfg.layers
+        D, Hd, N, H, Lr = cfg.width, cfg.hidden_pad, cfg.tokens, cfg.heads, cfg.layers   # Hd: padded hidden width
         M = B * N
         Mp = B * (N - 1)
         bf = dict(device=dev, dtype=torch.bfloat16)
@@ -126,8 +129,9 @@ class _Tape:
         self.aln = [torch.empty(M, D, **bf) for _ in range(Lr)]
         self.u2 = [torch.empty(M, D, **bf) for _ in range(Lr)]
         self.x12 = [torch.empty(M, 2 * Hd, **bf) for _ in range(Lr)]
-        self.h = [torch.empty(M, Hd, **bf) for _ in range(Lr)]
-        self.hln = [torch.empty(M, Hd, **bf) for _ in range(Lr)]
+        # padded hidden columns are never written by the LayerNorm / SwiGLU kernels: keep them exact zeros
+        self.h = [torch.zeros(M, Hd, **bf) for _ in range(Lr)]
+        self.hln = [torch.zeros(M, Hd, **bf) for _ in range(Lr)]
         self.stats = [[torch.empty(M, **f32) for _ in range(8)] for _ in range(Lr)]   # mean/rstd x 4 LNs
         self.tok_ln = torch.empty(Mp, D, **bf)
         self.tok_stats = [torch.empty(Mp, **f32) for _ in range(2)]
@@ -144,7 +148,7 @@ class _Tape:
         self.g_Hd = torch.empty(M, Hd, **bf)
         self.g_Hd2 = torch.empty(M, Hd, **bf)
         self.act_T_Hd = torch.empty(Hd, Mpad, **bf)
-        self.g_2Hd = torch.empty(M, 2 * Hd, **bf)
+        self.g_2Hd = torch.zeros(M, 2 * Hd, **bf)
         self.g_T_2Hd = torch.empty(2 * Hd, Mpad, **bf)
         self.g_3D = torch.empty(M, 3 * D, **bf)
         self.g_T_3D = torch.empty(3 * D, Mpad, **bf)
@@ -153,6 +157,7 @@ class _Tape:
         self.d_head = torch.empty(Mp, cfg.embed_dim, **f32)
         self.d_head_bf = torch.empty(Mp, cfg.embed_dim, **bf)
         self.col_ws = torch.empty(128 * 2 * max(3 * D, 2 * Hd), **f32)
+        self.dw3_pad = torch.zeros(D, Hd, **f32) if Hd != cfg.hidden else None    # wgrad scratch with aligned rows
 
 
 class StudentEngine:
@@ -161,10 +166,9 @@ class StudentEngine:
 
     def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device):
         L.require_device()
-        if cfg.hidden % 128 != 0:
-            raise NotImplementedError(f"training path with SwiGLU hidden {cfg.hidden} (ViT-L/14) needs the padded student "
-                                      "packs: inference / teacher are supported, training is next round (DESIGN.md §9)")
-        assert cfg.head_dim == 64
+        assert cfg.head_dim == 64 and cfg.hidden % 2 == 0
+        self.Hd, self.Hp = cfg.hidden, cfg.hidden_pad           # real / padded SwiGLU hidden width
+        self.padded = self.Hp != self.Hd
         self.cfg, self.device = cfg, device
         self.layout = FlatLayout(cfg)
         lay = self.layout
@@ -207,7 +211,7 @@ class StudentEngine:
 
     def _alloc_packs(self):
         cfg, dev = self.cfg, self.device
-        D, Hd = cfg.width, cfg.hidden
+        D, Hd = cfg.width, cfg.hidden_pad
         bf = dict(device=dev, dtype=torch.bfloat16)
         for i, pk in enumerate(self.packs):
             last = i == cfg.layers - 1
@@ -222,10 +226,12 @@ class StudentEngine:
                 pk.wvT = torch.empty(D, D, **bf)
             pk.wproj = torch.empty(D, D, **bf)
             pk.wprojT = torch.empty(D, D, **bf)
-            pk.w12 = torch.empty(2 * Hd, D, **bf)
-            pk.w12T = torch.empty(D, 2 * Hd, **bf)
-            pk.w3 = torch.empty(D, Hd, **bf)
-            pk.w3T = torch.empty(Hd, D, **bf)
+            # zero-initialised: the padded rows / columns (ViT-L) are never rewritten
+            pk.w12 = torch.zeros(2 * Hd, D, **bf)
+            pk.w12T = torch.zeros(D, 2 * Hd, **bf)
+            pk.b12 = torch.zeros(2 * Hd, device=dev, dtype=torch.float32)
+            pk.w3 = torch.zeros(D, Hd, **bf)
+            pk.w3T = torch.zeros(Hd, D, **bf)
 
     def p(self, i: int, name: str) -> Tensor:
         return self.layout.view(self.flat_param, f"blocks.{i}.{name}")
@@ -251,8 +257,15 @@ class StudentEngine:
             else:
                 ops.cast_transpose(self.p(i, "attn.v_proj.weight"), D, D, dst=pk.wv, dst_t=pk.wvT)
             ops.cast_transpose(self.p(i, "attn.proj.weight"), D, D, dst=pk.wproj, dst_t=pk.wprojT)
-            ops.cast_transpose(self._span(self.flat_param, i, "mlp.w1.weight", 2 * Hd, D), 2 * Hd, D,
-                               dst=pk.w12, dst_t=pk.w12T)
+            Hp = self.Hp
+            if not self.padded:
+                ops.cast_transpose(self._span(self.flat_param, i, "mlp.w1.weight", 2 * Hd, D), 2 * Hd, D,
+                                   dst=pk.w12, dst_t=pk.w12T)
+            else:   # [w1 | pad | w2 | pad] rows, transposed copy column blocks at 0 and Hp
+                ops.cast_transpose(self.p(i, "mlp.w1.weight"), Hd, D, dst=pk.w12[:Hd], dst_t=pk.w12T, ldt=2 * Hp)
+                ops.cast_transpose(self.p(i, "mlp.w2.weight"), Hd, D, dst=pk.w12[Hp:Hp + Hd], dst_t=pk.w12T[:, Hp:], ldt=2 * Hp)
+            pk.b12[:Hd].copy_(self.p(i, "mlp.w1.bias"))
+            pk.b12[Hp:Hp + Hd].copy_(self.p(i, "mlp.w2.bias"))
             ops.cast_transpose(self.p(i, "mlp.w3.weight"), D, Hd, dst=pk.w3, dst_t=pk.w3T)
 
     # ------------------------------------------------------------------ forward
@@ -291,9 +304,8 @@ class StudentEngine:
             ops.gemm(t.aln[i], pk.wproj, t.xmid[i], M=M, bias=self.p(i, "attn.proj.bias"), residual=x)
             ops.layernorm_fwd(t.xmid[i], M, D, self.p(i, "norm2.weight"), self.p(i, "norm2.bias"), eps, t.u2[i],
                               mean=st[4], rstd=st[5])
-            b12 = self._span(self.flat_param, i, "mlp.w1.bias", 1, 2 * Hd).view(-1)
-            ops.gemm(t.u2[i], pk.w12, t.x12[i], M=M, bias=b12)
-            ops.swiglu_fwd(t.x12[i], M, Hd, t.h[i], split=True)
+            ops.gemm(t.u2[i], pk.w12, t.x12[i], M=M, bias=pk.b12)
+            ops.swiglu_fwd(t.x12[i], M, Hd, t.h[i], split=self.Hp if self.padded else True)
             ops.layernorm_fwd(t.h[i], M, Hd, self.p(i, "mlp.ffn_ln.weight"), self.p(i, "mlp.ffn_ln.bias"), eps, t.hln[i],
                               mean=st[6], rstd=st[7])
             ops.gemm(t.hln[i], pk.w3, t.x[i + 1], M=M, bias=self.p(i, "mlp.w3.bias"), residual=t.xmid[i])
@@ -332,18 +344,30 @@ class StudentEngine:
             # ---- MLP branch: x_out = xmid + w3(hln) + b3
             ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
             ops.col_reduce(dx, M, D, self.g(i, "mlp.w3.bias"), ws)
-            ops.cast_transpose(t.hln[i], M, Hd, dst_t=t.act_T_Hd)
-            ops.gemm(t.g_T_D, t.act_T_Hd, self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M, k_splits=-1)           # dW3 = dx^T hln
+            ops.cast_transpose(t.hln[i], M, self.Hp, dst_t=t.act_T_Hd)
+            if not self.padded:
+                ops.gemm(t.g_T_D, t.act_T_Hd, self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M, k_splits=-1)       # dW3 = dx^T hln
+            else:   # rows of the [D, 2730] gradient are not 16 B aligned: GEMM into a padded scratch, then copy
+                t.dw3_pad.zero_()
+                ops.gemm(t.g_T_D, t.act_T_Hd, t.dw3_pad, M=D, N=self.Hp, K=M, k_splits=-1)
+                self.g(i, "mlp.w3.weight").copy_(t.dw3_pad[:, :Hd])
             ops.gemm(t.g_bf_D, pk.w3T, t.g_Hd, M=M)                                               # d_hln
             ops.col_reduce(t.g_Hd, M, Hd, self.g(i, "mlp.ffn_ln.bias"), ws, x=t.h[i], mean=st[6], rstd=st[7],
                            dgamma=self.g(i, "mlp.ffn_ln.weight"))
             ops.layernorm_bwd_dx(t.g_Hd, t.h[i], M, Hd, st[6], st[7], self.p(i, "mlp.ffn_ln.weight"), t.g_Hd2)  # d_h
-            ops.swiglu_bwd(t.x12[i], t.g_Hd2, M, Hd, t.g_2Hd, split=True)                         # d_x12
-            ops.cast_transpose(t.g_2Hd, M, 2 * Hd, dst_t=t.g_T_2Hd)
+            ops.swiglu_bwd(t.x12[i], t.g_Hd2, M, Hd, t.g_2Hd, split=self.Hp if self.padded else True)   # d_x12
+            ops.cast_transpose(t.g_2Hd, M, 2 * self.Hp, dst_t=t.g_T_2Hd)
             ops.cast_transpose(t.u2[i], M, D, dst_t=t.act_T_D)
-            ops.gemm(t.g_T_2Hd, t.act_T_D, self._span(self.flat_grad, i, "mlp.w1.weight", 2 * Hd, D),
-                     M=2 * Hd, N=D, K=M, k_splits=-1)                                             # dW1|dW2
-            ops.col_reduce(t.g_2Hd, M, 2 * Hd, self._span(self.flat_grad, i, "mlp.w1.bias", 1, 2 * Hd).view(-1), ws)
+            if not self.padded:
+                ops.gemm(t.g_T_2Hd, t.act_T_D, self._span(self.flat_grad, i, "mlp.w1.weight", 2 * Hd, D),
+                         M=2 * Hd, N=D, K=M, k_splits=-1)                                         # dW1|dW2
+                ops.col_reduce(t.g_2Hd, M, 2 * Hd, self._span(self.flat_grad, i, "mlp.w1.bias", 1, 2 * Hd).view(-1), ws)
+            else:
+                Hp = self.Hp
+                ops.gemm(t.g_T_2Hd[:Hd], t.act_T_D, self.g(i, "mlp.w1.weight"), M=Hd, N=D, K=M, k_splits=-1)
+                ops.gemm(t.g_T_2Hd[Hp:Hp + Hd], t.act_T_D, self.g(i, "mlp.w2.weight"), M=Hd, N=D, K=M, k_splits=-1)
+                ops.col_reduce(t.g_2Hd, M, Hd, self.g(i, "mlp.w1.bias"), ws, lddy=2 * Hp)
+                ops.col_reduce(t.g_2Hd[:, Hp:], M, Hd, self.g(i, "mlp.w2.bias"), ws, lddy=2 * Hp)
             ops.gemm(t.g_2Hd, pk.w12T, t.g_D2, M=M)                                               # d_u2
             ops.col_reduce(t.g_D2, M, D, self.g(i, "norm2.bias"), ws, x=t.xmid[i], mean=st[4], rstd=st[5],
                            dgamma=self.g(i, "norm2.weight"))

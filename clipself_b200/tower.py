@@ -204,7 +204,7 @@ class TowerEngine:
         patches = ops.im2col_patches(images, cfg.patch, w.k_pe_pad)
         ops.gemm(patches, w.pe_w, x, M=B * (cfg.tokens - 1), N=cfg.width, K=w.k_pe_pad, mode=L.EPI_TOKENS,
                  bias=w.pe_b, pos_embed=w.pos, tokens=cfg.tokens)
-        ops.fill_cls_rows(w.cls, w.pos, x.view(B, cfg.tokens, cfg.width))
+        ops.fill_cls_rows(w.cls, w.pos, x[:B * cfg.tokens].view(B, cfg.tokens, cfg.width))
 
     def block_inplace(self, i: int, ws: Workspace, B: int, with_attention: bool = True) -> None:
         """One residual block on ws.x in place (inference; nothing saved)."""

@@ -227,7 +227,8 @@ int cs_col_reduce(const void* dy, cs_dtype_t dy_dtype, int64_t lddy, const void*
                   float* workspace, int64_t workspace_floats, void* stream);
 
 /* SwiGLU (eva_vit_model.py:98-101) on pre-activations x12 [M, 2*Hd] bf16:
- *   split_layout != 0: gate = x12[:, j], up = x12[:, Hd + j]           (weights [w1; w2] stacked)
+ *   split_layout == 1: gate = x12[:, j], up = x12[:, Hd + j]           (weights [w1; w2] stacked)
+ *   split_layout >= 2: gate = x12[:, j], up = x12[:, split_layout + j] (padded halves, ViT-L: Hd 2730 -> 2816)
  *   split_layout == 0: the packed layout of cs_pack_swiglu_weights (gate|up interleaved by 128)
  *   h = silu(gate) * up  and its backward (dx12 in the same layout as x12). */
 int cs_swiglu_fwd(const void* x12_bf16, int64_t M, int Hd, int64_t ld12, void* h_bf16, int64_t ldh,

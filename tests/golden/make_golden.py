@@ -142,6 +142,6 @@ if __name__ == "__main__":
     # BASELINE.json configs[0]: ViT-B/16, 2x224x224, 8 patch-boxes/img
     run_case("cfg1_b16", O.CFG_B16, "EVA02-CLIP-B-16", batch=2, K=8, kind="grid", ragged=False, seed=300,
              store_inputs=False, store_all_grads=False, tap_blocks=(0, 10))
-    # BASELINE.json configs[3]/[4] architecture (EVA02 ViT-L/14 @336), forward only, 1 image x 2 boxes
+    # BASELINE.json configs[3]/[4] architecture (EVA02 ViT-L/14 @336), 1 image x 2 boxes, forward + backward
     run_case("l14_fwd", O.CFG_L14_336, "EVA02-CLIP-L-14-336", batch=1, K=2, kind="proposal", ragged=False, seed=400,
-             store_inputs=False, store_all_grads=False, tap_blocks=(0,), backward=False)
+             store_inputs=False, store_all_grads=False, tap_blocks=(0,), backward=True)

@@ -11,7 +11,7 @@ from oracle import clipself_oracle as O
 pytestmark = pytest.mark.gpu
 
 CASES = {"tiny_ragged": (O.CFG_TINY, 3, 5, "proposal", True), "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
-         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False)}
+         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False), "l14_fwd": (O.CFG_L14_336, 1, 2, "proposal", False)}
 
 
 def build_model(ocfg, seed, dev):
@@ -30,7 +30,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("tag,host_batch", [("tiny_ragged", True), ("tiny_ragged", False), ("tiny_grid", True),
-                                            ("cfg1_b16", True)])
+                                            ("cfg1_b16", True), ("l14_fwd", True)])
 def test_step_vs_golden(golden, tag, host_batch):
     from clipself_b200.training.clipself import CLIPSelf
     ocfg, B, K, kind, ragged = CASES[tag]

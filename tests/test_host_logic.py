@@ -136,3 +136,28 @@ def test_fused_adamw_group_bookkeeping():
     for g in opt.param_groups:
         g["lr"] = 5e-4                                       # what scheduler.py:4-6 does
     assert opt.exp_avg.numel() == 12 and opt.state_dict()["step"] == 0
+
+
+def test_open_clip_namespace_and_cliploss():
+    """`import open_clip` / `training.clipself` resolve through compat/ ; ClipLoss matches the formula."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    try:
+        import open_clip
+        from training.clipself import CLIPSelf
+        assert callable(open_clip.create_model) and CLIPSelf is not None
+        g = torch.Generator().manual_seed(0)
+        img = torch.nn.functional.normalize(torch.randn(6, 16, generator=g), dim=-1)
+        txt = torch.nn.functional.normalize(torch.randn(6, 16, generator=g), dim=-1)
+        loss = open_clip.ClipLoss()(img, txt, torch.tensor(10.0))
+        logits = 10.0 * img @ txt.T
+        ref = (torch.nn.functional.cross_entropy(logits, torch.arange(6)) +
+               torch.nn.functional.cross_entropy(logits.T, torch.arange(6))) / 2
+        assert torch.allclose(loss, ref)
+        assert set(open_clip.ClipLoss()(img, txt, torch.tensor(10.0), output_dict=True)) == {"contrastive_loss"}
+    finally:
+        sys.path.remove(os.path.join(root, "compat"))
+        for m in [k for k in sys.modules if k == "open_clip" or k.startswith("training")]:
+            sys.modules.pop(m, None)
