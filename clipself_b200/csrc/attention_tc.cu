@@ -178,6 +178,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         const int nchunks = (p.nkp + 31) / 32;
         const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
         const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+        const int n_keys = p.N, full_chunks = p.N / 32;
+        const float scale_log2 = p.scale_log2;
         float* xmax = xch;                                         // [2][128]
         float* xsum = xch + 256;                                   // [2][128]
         // row max of one tile (this thread's share of the key columns, then exchanged with the partner warp)
@@ -190,9 +192,14 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 uint32_t v[32];
                 tmem_ld32(ts + c * 32, v);
                 tmem_ld_wait();
+                if (c < full_chunks) {                    // all 32 keys valid: no per-element predicate
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c * 32 + j < n_keys) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
             }
             xmax[half * 128 + r] = mx;
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -204,7 +211,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             const int item = blockIdx.x + il * gridDim.x;
             const int b = item / p.H, h = item % p.H;
             const uint32_t ts = tmem_base + lane_addr + (uint32_t)((tt & 1) * S_STRIDE);
-            const float mxs = mx * p.scale_log2;
+            const float mxs = mx * scale_log2;
             // P buffer must have been consumed by the previous tile's PV
             mbar_wait(p_empty, ((uint32_t)tt & 1u) ^ 1u);
             float sum = 0.f;
@@ -213,11 +220,18 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 tmem_ld32(ts + c * 32, v);
                 tmem_ld_wait();
                 float pr[32];
+                if (c < full_chunks) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = (c * 32 + j < p.N) ? ex2(__uint_as_float(v[j]) * p.scale_log2 - mxs) : 0.f;
-                    pr[j] = e;
-                    sum += e;
+                    for (int j = 0; j < 32; ++j) {
+                        pr[j] = ex2(__uint_as_float(v[j]) * scale_log2 - mxs);
+                        sum += pr[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        pr[j] = (c * 32 + j < n_keys) ? ex2(__uint_as_float(v[j]) * scale_log2 - mxs) : 0.f;
+                        sum += pr[j];
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
