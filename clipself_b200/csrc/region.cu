@@ -105,13 +105,31 @@ __global__ void roi_weights_kernel(const float* __restrict__ rois, int R, int H,
 constexpr int ROI_CS = 64;       // channel slice per CTA
 constexpr int ROI_LANES = 4;     // roi (or pixel) lanes per CTA
 constexpr int ROI_THREADS = ROI_CS * ROI_LANES;
+constexpr int ROI_CHUNK = 64;    // rois whose separable weights are staged in shared memory at once
 
-// out[r, c] = sum_{y,x} wy[r,y] wx[r,x] f[b,y,x,c];  grid (C/64, B)
+// first / last index with a non-zero weight (the support of a box along one axis is contiguous)
+__device__ __forceinline__ void support(const float* __restrict__ w, int n, int& lo, int& hi) {
+    lo = n;
+    hi = -1;
+    for (int i = 0; i < n; ++i)
+        if (w[i] != 0.f) {
+            if (lo == n) lo = i;
+            hi = i;
+        }
+}
+
+// out[r, c] = sum_{y,x} wy[r,y] wx[r,x] f[b,y,x,c];  grid (C/64, B).
+// The image's map slice [H*W][64] is staged in shared memory once (kStage) — every map byte crosses HBM
+// exactly once — together with the separable weights of up to 64 of its boxes; each box then only walks
+// the pixels of its support window.
 template <bool kStage>
 __global__ void __launch_bounds__(ROI_THREADS)
 roi_align_fwd_kernel(const float* __restrict__ fmap, int H, int W, int C, const int* __restrict__ img_offsets,
                      const float* __restrict__ wy, const float* __restrict__ wx, float* __restrict__ out) {
-    extern __shared__ float s_map[];   // [H*W][ROI_CS] when staged
+    extern __shared__ float s_dyn[];
+    float* s_wy = s_dyn;                             // [ROI_CHUNK][H]
+    float* s_wx = s_wy + ROI_CHUNK * H;              // [ROI_CHUNK][W]
+    float* s_map = s_wx + ROI_CHUNK * W;             // [H*W][ROI_CS] when staged
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * ROI_CS;
     const int c = threadIdx.x % ROI_CS;
@@ -121,43 +139,54 @@ roi_align_fwd_kernel(const float* __restrict__ fmap, int H, int W, int C, const 
     const float* g = fmap + (long long)b * H * W * C + c0;
     const bool c_ok = c0 + c < C;
     if (kStage) {
-        for (int i = threadIdx.x; i < H * W * ROI_CS; i += ROI_THREADS) {
-            const int p = i / ROI_CS, cc = i % ROI_CS;
-            s_map[i] = (c0 + cc < C) ? g[(long long)p * C + cc] : 0.f;
+        for (int i = threadIdx.x; i < H * W * (ROI_CS / 4); i += ROI_THREADS) {      // float4 per thread
+            const int p = i / (ROI_CS / 4), c4 = (i % (ROI_CS / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + c4 + 3 < C) v = *reinterpret_cast<const float4*>(g + (long long)p * C + c4);
+            else
+                for (int z = 0; z < 4; ++z)
+                    if (c0 + c4 + z < C) (&v.x)[z] = g[(long long)p * C + c4 + z];
+            *reinterpret_cast<float4*>(s_map + p * ROI_CS + c4) = v;
         }
-        __syncthreads();
     }
-    for (int r = begin + lane; r < end; r += ROI_LANES) {
-        const float* wyr = wy + (long long)r * H;
-        const float* wxr = wx + (long long)r * W;
-        float acc = 0.f;
-        for (int y = 0; y < H; ++y) {
-            const float a = wyr[y];
-            if (a == 0.f) continue;
-            float row = 0.f;
-            for (int x = 0; x < W; ++x) {
-                const float bx = wxr[x];
-                if (bx == 0.f) continue;
-                const float f = kStage ? s_map[(y * W + x) * ROI_CS + c]
-                                       : (c_ok ? g[(long long)(y * W + x) * C + c] : 0.f);
-                row = fmaf(bx, f, row);
+    for (int r0 = begin; r0 < end; r0 += ROI_CHUNK) {
+        const int n = min(ROI_CHUNK, end - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * H; i += ROI_THREADS) s_wy[i] = wy[(long long)r0 * H + i];
+        for (int i = threadIdx.x; i < n * W; i += ROI_THREADS) s_wx[i] = wx[(long long)r0 * W + i];
+        __syncthreads();
+        for (int rr = lane; rr < n; rr += ROI_LANES) {
+            const float* wyr = s_wy + rr * H;
+            const float* wxr = s_wx + rr * W;
+            int ylo, yhi, xlo, xhi;
+            support(wyr, H, ylo, yhi);
+            support(wxr, W, xlo, xhi);
+            float acc = 0.f;
+            for (int y = ylo; y <= yhi; ++y) {
+                float row = 0.f;
+                for (int x = xlo; x <= xhi; ++x) {
+                    const float f = kStage ? s_map[(y * W + x) * ROI_CS + c] : (c_ok ? g[(long long)(y * W + x) * C + c] : 0.f);
+                    row = fmaf(wxr[x], f, row);
+                }
+                acc = fmaf(wyr[y], row, acc);
             }
-            acc = fmaf(a, row, acc);
+            if (c_ok) out[(long long)(r0 + rr) * C + c0 + c] = acc;
         }
-        if (c_ok) out[(long long)r * C + c0 + c] = acc;
     }
 }
 
-// d_fmap[b,y,x,c] = sum_{r in image b} wy[r,y] wx[r,x] d_out[r,c];  grid (C/64, B).  Gather form:
-// deterministic, every d_fmap element written exactly once.
+// d_fmap[b,y,x,c] = sum_{r in image b} wy[r,y] wx[r,x] d_out[r,c];  grid (C/64, B).
+// The image's gradient slice [H*W][64] is accumulated in shared memory, box after box in index order
+// (deterministic, no atomics: inside one box every (pixel, channel) belongs to one thread), and written
+// to HBM once.
+template <bool kStage>
 __global__ void __launch_bounds__(ROI_THREADS)
 roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const int* __restrict__ img_offsets,
                      const float* __restrict__ wy, const float* __restrict__ wx, float* __restrict__ d_fmap) {
-    extern __shared__ float s_buf[];   // per roi chunk: d_out [32][ROI_CS], wy [32][H], wx [32][W]
-    constexpr int CH = 32;
-    float* s_do = s_buf;
-    float* s_wy = s_do + CH * ROI_CS;
-    float* s_wx = s_wy + CH * H;
+    extern __shared__ float s_dyn[];
+    float* s_wy = s_dyn;
+    float* s_wx = s_wy + ROI_CHUNK * H;
+    float* s_acc = s_wx + ROI_CHUNK * W;             // [H*W][ROI_CS] when staged
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * ROI_CS;
     const int c = threadIdx.x % ROI_CS;
@@ -166,70 +195,101 @@ roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const
     const bool c_ok = c0 + c < C;
     float* g = d_fmap + (long long)b * H * W * C + c0;
     const int HW = H * W;
-    if (begin == end) {                      // image without boxes: its gradient slice is zero
+    if (kStage) {
+        for (int i = threadIdx.x; i < HW * ROI_CS; i += ROI_THREADS) s_acc[i] = 0.f;
+    } else {
         for (int p = lane; p < HW; p += ROI_LANES)
             if (c_ok) g[(long long)p * C + c] = 0.f;
-        return;
     }
-    // rois are processed in chunks of CH staged in shared memory; images with more than CH rois
-    // accumulate the later chunks onto the slice written by the first one (same thread, no race).
-    for (int r0 = begin; r0 < end; r0 += CH) {
-        const int n = min(CH, end - r0);
+    for (int r0 = begin; r0 < end; r0 += ROI_CHUNK) {
+        const int n = min(ROI_CHUNK, end - r0);
         __syncthreads();
-        for (int i = threadIdx.x; i < n * ROI_CS; i += ROI_THREADS) {
-            const int rr = i / ROI_CS, cc = i % ROI_CS;
-            s_do[i] = (c0 + cc < C) ? d_out[(long long)(r0 + rr) * C + c0 + cc] : 0.f;
-        }
         for (int i = threadIdx.x; i < n * H; i += ROI_THREADS) s_wy[i] = wy[(long long)r0 * H + i];
         for (int i = threadIdx.x; i < n * W; i += ROI_THREADS) s_wx[i] = wx[(long long)r0 * W + i];
         __syncthreads();
-        for (int p = lane; p < HW; p += ROI_LANES) {
-            const int y = p / W, x = p % W;
-            float acc = 0.f;
-            for (int rr = 0; rr < n; ++rr) {
-                const float wgt = s_wy[rr * H + y] * s_wx[rr * W + x];
-                acc = fmaf(wgt, s_do[rr * ROI_CS + c], acc);
+        for (int rr = 0; rr < n; ++rr) {            // boxes in order; the 4 lanes split the window's pixels
+            const float* wyr = s_wy + rr * H;
+            const float* wxr = s_wx + rr * W;
+            int ylo, yhi, xlo, xhi;
+            support(wyr, H, ylo, yhi);
+            support(wxr, W, xlo, xhi);
+            const float go = c_ok ? d_out[(long long)(r0 + rr) * C + c0 + c] : 0.f;
+            const int ww = max(xhi - xlo + 1, 0);                  // degenerate boxes have an empty support
+            const int npx = max(yhi - ylo + 1, 0) * ww;
+            for (int q = lane; q < npx; q += ROI_LANES) {
+                const int y = ylo + q / ww, x = xlo + q % ww;
+                const float v = wyr[y] * wxr[x] * go;
+                if (kStage) s_acc[(y * W + x) * ROI_CS + c] += v;
+                else if (c_ok) g[(long long)(y * W + x) * C + c] += v;
             }
-            if (c_ok) {
-                float* dst = g + (long long)p * C + c;
-                *dst = (r0 == begin) ? acc : (*dst + acc);
-            }
+            if (npx > 0) __syncthreads();            // the next box may overlap this one's pixels (other lanes)
+        }
+    }
+    if (kStage) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < HW * (ROI_CS / 4); i += ROI_THREADS) {
+            const int p = i / (ROI_CS / 4), c4 = (i % (ROI_CS / 4)) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(s_acc + p * ROI_CS + c4);
+            if (c0 + c4 + 3 < C) *reinterpret_cast<float4*>(g + (long long)p * C + c4) = v;
+            else
+                for (int z = 0; z < 4; ++z)
+                    if (c0 + c4 + z < C) g[(long long)p * C + c4 + z] = (&v.x)[z];
         }
     }
 }
 
-// out[r,c] = sum_p m[r,p] f[b,p,c] / (sum_p m[r,p] + 1e-12);  grid (C/64, B)
-template <bool kStage>
+// out[r,c] = sum_p m[r,p] f[b,p,c] / (sum_p m[r,p] + 1e-12);  grid (C/64, B).
+// Pixel chunks of the map slice and of the image's masks are staged in shared memory; every thread keeps
+// the accumulators of its boxes (one channel, every 4th box) in registers.
+constexpr int MP_PX = 64;        // pixels per staged chunk
+constexpr int MP_ACC = 16;       // boxes per thread per pass (x 4 lanes = 64 boxes per pass)
 __global__ void __launch_bounds__(ROI_THREADS)
 mask_pool_kernel(const float* __restrict__ fmap, int HW, int C, const float* __restrict__ masks,
                  const int* __restrict__ img_offsets, float* __restrict__ out) {
-    extern __shared__ float s_map[];
+    __shared__ float s_f[MP_PX][ROI_CS];
+    __shared__ float s_m[MP_ACC * ROI_LANES][MP_PX + 1];
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * ROI_CS;
     const int c = threadIdx.x % ROI_CS;
     const int lane = threadIdx.x / ROI_CS;
     const int begin = img_offsets[b], end = img_offsets[b + 1];
-    if (begin == end) return;
     const float* g = fmap + (long long)b * HW * C + c0;
     const bool c_ok = c0 + c < C;
-    if (kStage) {
-        for (int i = threadIdx.x; i < HW * ROI_CS; i += ROI_THREADS) {
-            const int p = i / ROI_CS, cc = i % ROI_CS;
-            s_map[i] = (c0 + cc < C) ? g[(long long)p * C + cc] : 0.f;
+    for (int r0 = begin; r0 < end; r0 += MP_ACC * ROI_LANES) {
+        const int n = min(MP_ACC * ROI_LANES, end - r0);
+        float acc[MP_ACC], msum[MP_ACC];
+#pragma unroll
+        for (int k = 0; k < MP_ACC; ++k) acc[k] = msum[k] = 0.f;
+        for (int p0 = 0; p0 < HW; p0 += MP_PX) {
+            const int np = min(MP_PX, HW - p0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < np * ROI_CS; i += ROI_THREADS) {
+                const int p = i / ROI_CS, cc = i % ROI_CS;
+                s_f[p][cc] = (c0 + cc < C) ? g[(long long)(p0 + p) * C + cc] : 0.f;
+            }
+            for (int i = threadIdx.x; i < n * np; i += ROI_THREADS) {
+                const int rr = i / np, p = i % np;
+                s_m[rr][p] = masks[(long long)(r0 + rr) * HW + p0 + p];
+            }
+            __syncthreads();
+            for (int p = 0; p < np; ++p) {
+                const float f = s_f[p][c];
+#pragma unroll
+                for (int k = 0; k < MP_ACC; ++k) {
+                    const int rr = k * ROI_LANES + lane;
+                    if (rr < n) {
+                        const float w = s_m[rr][p];
+                        acc[k] = fmaf(w, f, acc[k]);
+                        msum[k] += w;
+                    }
+                }
+            }
         }
-        __syncthreads();
-    }
-    for (int r = begin + lane; r < end; r += ROI_LANES) {
-        const float* m = masks + (long long)r * HW;
-        float acc = 0.f, msum = 0.f;
-        for (int p = 0; p < HW; ++p) {
-            const float w = m[p];
-            msum += w;
-            if (w == 0.f) continue;
-            const float f = kStage ? s_map[p * ROI_CS + c] : (c_ok ? g[(long long)p * C + c] : 0.f);
-            acc = fmaf(w, f, acc);
+#pragma unroll
+        for (int k = 0; k < MP_ACC; ++k) {
+            const int rr = k * ROI_LANES + lane;
+            if (rr < n && c_ok) out[(long long)(r0 + rr) * C + c0 + c] = acc[k] / (msum[k] + 1e-12f);
         }
-        if (c_ok) out[(long long)r * C + c0 + c] = acc / (msum + 1e-12f);
     }
 }
 
@@ -376,30 +436,32 @@ extern "C" int cs_gather_rows(const void* src, const int32_t* index, int R, int6
     return CS_OK;
 }
 
-static int stage_bytes(int hw) { return hw * ROI_CS * (int)sizeof(float); }
+static int roi_smem_bytes(int H, int W, bool stage) {
+    return (ROI_CHUNK * (H + W) + (stage ? H * W * ROI_CS : 0)) * (int)sizeof(float);
+}
 constexpr int kMaxStage = 200 * 1024;
 
 extern "C" int cs_roi_align_fwd(const float* fmap, int B, int H, int W, int C, const float* rois,
                                 const int32_t* img_offsets, int R, float* wy, float* wx, float* out,
                                 void* stream) {
     CS_CHECK_ARG(fmap && rois && img_offsets && wy && wx && out, "cs_roi_align_fwd: null pointer");
-    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0, "cs_roi_align_fwd: bad shape");
+    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 512, "cs_roi_align_fwd: bad shape");
+    CS_CHECK_ARG((uintptr_t)fmap % 16 == 0 && C % 4 == 0, "cs_roi_align_fwd: fmap must be 16 B aligned, C %% 4 == 0");
     if (R == 0) return CS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     roi_weights_kernel<<<ceil_div(R, 128), 128, 0, st>>>(rois, R, H, W, wy, wx);
     CS_LAUNCH_CHECK();
     dim3 grid(ceil_div(C, ROI_CS), B);
-    const int smem = stage_bytes(H * W);
-    if (smem <= kMaxStage) {
-        static bool configured = false;
-        if (!configured) {
-            CS_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
-            configured = true;
-        }
-        roi_align_fwd_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fmap, H, W, C, img_offsets, wy, wx, out);
-    } else {
-        roi_align_fwd_kernel<false><<<grid, ROI_THREADS, 0, st>>>(fmap, H, W, C, img_offsets, wy, wx, out);
+    const bool stage = roi_smem_bytes(H, W, true) <= kMaxStage;
+    const int smem = roi_smem_bytes(H, W, stage);
+    static bool configured = false;
+    if (!configured) {
+        CS_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+        CS_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+        configured = true;
     }
+    if (stage) roi_align_fwd_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fmap, H, W, C, img_offsets, wy, wx, out);
+    else roi_align_fwd_kernel<false><<<grid, ROI_THREADS, smem, st>>>(fmap, H, W, C, img_offsets, wy, wx, out);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -407,12 +469,20 @@ extern "C" int cs_roi_align_fwd(const float* fmap, int B, int H, int W, int C, c
 extern "C" int cs_roi_align_bwd(const float* d_out, int B, int H, int W, int C, const int32_t* img_offsets,
                                 int R, const float* wy, const float* wx, float* d_fmap, void* stream) {
     CS_CHECK_ARG(d_out && img_offsets && wy && wx && d_fmap, "cs_roi_align_bwd: null pointer");
-    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0, "cs_roi_align_bwd: bad shape");
+    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 512, "cs_roi_align_bwd: bad shape");
+    CS_CHECK_ARG((uintptr_t)d_fmap % 16 == 0 && C % 4 == 0, "cs_roi_align_bwd: d_fmap must be 16 B aligned, C %% 4 == 0");
     dim3 grid(ceil_div(C, ROI_CS), B);
-    const int smem = (32 * ROI_CS + 32 * H + 32 * W) * (int)sizeof(float);
-    CS_CHECK_ARG(smem <= 48 * 1024, "cs_roi_align_bwd: H+W too large (%d,%d)", H, W);
-    roi_align_bwd_kernel<<<grid, ROI_THREADS, smem, (cudaStream_t)stream>>>(d_out, H, W, C, img_offsets, wy, wx,
-                                                                           d_fmap);
+    const bool stage = roi_smem_bytes(H, W, true) <= kMaxStage;
+    const int smem = roi_smem_bytes(H, W, stage);
+    static bool configured = false;
+    if (!configured) {
+        CS_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+        CS_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
+        configured = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stage) roi_align_bwd_kernel<true><<<grid, ROI_THREADS, smem, st>>>(d_out, H, W, C, img_offsets, wy, wx, d_fmap);
+    else roi_align_bwd_kernel<false><<<grid, ROI_THREADS, smem, st>>>(d_out, H, W, C, img_offsets, wy, wx, d_fmap);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -422,19 +492,8 @@ extern "C" int cs_mask_pool_fwd(const float* fmap, int B, int HW, int C, const f
     CS_CHECK_ARG(fmap && masks && img_offsets && out, "cs_mask_pool_fwd: null pointer");
     CS_CHECK_ARG(B > 0 && HW > 0 && C > 0 && R >= 0, "cs_mask_pool_fwd: bad shape");
     if (R == 0) return CS_OK;
-    cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ceil_div(C, ROI_CS), B);
-    const int smem = stage_bytes(HW);
-    if (smem <= kMaxStage) {
-        static bool configured = false;
-        if (!configured) {
-            CS_CUDA(cudaFuncSetAttribute(mask_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
-            configured = true;
-        }
-        mask_pool_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fmap, HW, C, masks, img_offsets, out);
-    } else {
-        mask_pool_kernel<false><<<grid, ROI_THREADS, 0, st>>>(fmap, HW, C, masks, img_offsets, out);
-    }
+    mask_pool_kernel<<<grid, ROI_THREADS, 0, (cudaStream_t)stream>>>(fmap, HW, C, masks, img_offsets, out);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

@@ -110,3 +110,44 @@ def test_l2norm_fwd_bwd(dev):
     np.testing.assert_allclose(y.cpu().numpy(), y_ref.detach().numpy(), rtol=1e-5, atol=1e-7)
     dx = ops.l2norm_bwd(y, inv, g.to(dev))
     np.testing.assert_allclose(dx.cpu().numpy(), x.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_roi_align_degenerate_and_empty_images(dev):
+    """Zero-area / inverted boxes pool to 0 (torchvision: empty sampling grid), images without boxes get a
+    zero gradient slice, and the oracle agrees."""
+    from clipself_b200 import ops
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(4)
+    B, H, W, C = 3, 5, 6, 64
+    fmap = torch.randn(B, H, W, C)
+    boxes = torch.zeros(B, 4, 5)
+    boxes[0, 0] = torch.tensor([0.2, 0.2, 0.2, 0.2, 1.0])      # zero area
+    boxes[0, 1] = torch.tensor([0.6, 0.7, 0.3, 0.1, 1.0])      # inverted
+    boxes[0, 2] = torch.tensor([0.0, 0.0, 1.0, 1.0, 1.0])
+    boxes[2, 0] = torch.tensor([0.1, 0.3, 0.9, 0.8, 1.0])      # image 1 has no valid box at all
+    rois, _, _, offsets = ops.extract_rois(boxes.to(dev))
+    R = int(offsets[-1])
+    assert offsets.cpu().tolist() == [0, 3, 3, 4]
+    out, wy, wx = ops.roi_align_fwd(fmap.to(dev), rois, offsets, R)
+    rois_list, _ = O.extract_rois(boxes)
+    den = O.denormalize_boxes(rois_list, H, W)
+    ref = tv.ops.roi_align(fmap.permute(0, 3, 1, 2).contiguous(), den, (1, 1), 1.0, -1, True)[..., 0, 0]
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-6)
+    assert float(out[1].abs().max()) == 0.0
+    d_fmap = ops.roi_align_bwd(torch.ones(R, C, device=dev), (B, H, W, C), offsets, R, wy, wx)
+    assert float(d_fmap[1].abs().max()) == 0.0 and float(d_fmap[2].abs().max()) > 0
+
+
+def test_mask_pool_empty_mask_and_large_extract(dev):
+    from clipself_b200 import ops
+    fmap = torch.randn(2, 9, 32, device=dev)
+    masks = torch.zeros(3, 9, device=dev)
+    masks[1, 4] = 1.0
+    out = ops.mask_pool_fwd(fmap, masks, torch.tensor([0, 2, 3], dtype=torch.int32, device=dev))
+    assert float(out[0].abs().max()) == 0.0 and torch.allclose(out[1], fmap[0, 4]) and float(out[2].abs().max()) == 0.0
+    _, boxes, _ = O.synth_batch(O.CFG_TINY, 512, 64, 3, kind="proposal", ragged=True, crop_size=2)
+    rois_ref, idx_ref = O.extract_rois(boxes)
+    rois, crop_index, _, offsets = ops.extract_rois(boxes.to(dev))
+    R = int(offsets[-1])
+    assert R == idx_ref.numel() and torch.equal(rois[:R].cpu(), torch.cat(rois_ref))
+    assert crop_index[:R].cpu().tolist() == idx_ref.tolist()

@@ -61,6 +61,7 @@ def test_im2col(dev, dtype, S, P):
 def test_attention_fwd(dev, B, N, H):
     from clipself_b200 import ops
     D = H * 64
+    torch.manual_seed(1000 * B + 10 * N + H)
     qkv = torch.randn(B * N, 3 * D, device=dev).to(torch.bfloat16)
     out = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, H, N, device=dev)
@@ -77,6 +78,8 @@ def test_attention_fwd(dev, B, N, H):
         out2 = torch.empty_like(out)
         ops.attention_fwd(qkv, B, N, H, 0.125, out2, None, stats)
         assert torch.equal(out2, out)
-        o = out.float().view(B * N, 2 * H, 32)
-        torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=5e-3, atol=1e-2)      # taken before bf16 rounding
-        torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=5e-3, atol=1e-2)
+        # the statistics are taken from the f32 accumulators before the bf16 rounding of the output:
+        # compare with the f32 reference, tolerance = 32 elements x the kernel's per-element error
+        o = ref.view(B * N, 2 * H, 32)
+        torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-2, atol=5e-2)
+        torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-2, atol=5e-2)

@@ -122,3 +122,22 @@ def test_consecutive_ragged_steps_reuse_workspaces(monkeypatch):
         print(f"step {step}: B={B} K={K} loss {got:.6f} oracle {ref:.6f}")
         assert bs == B and abs(got - ref) <= 3e-3 * abs(ref), (step, got, ref)
         student.zero_grad(set_to_none=True)
+
+
+def test_step_with_an_image_without_boxes():
+    """An image whose rows are all padding (valid flag 0) contributes no RoI, no crop and no gradient."""
+    from clipself_b200.training.clipself import CLIPSelf
+    ocfg = O.CFG_TINY
+    dev = torch.device("cuda")
+    student, teacher = build_model(ocfg, 41, dev), build_model(ocfg, 42, dev)
+    student.lock_image_tower(unlocked_groups=ocfg.layers)
+    images, boxes, crops = O.synth_batch(ocfg, 3, 4, 77, kind="grid", ragged=False)
+    boxes[1] = 0.0
+    args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=0.5)
+    losses, bs, _ = CLIPSelf()((images, boxes, crops), student, teacher, None, dev, None, False, args)
+    losses["loss_cosine"].backward()
+    ref = O.clipself_step(O.synth_tower_weights(ocfg, 41), O.synth_tower_weights(ocfg, 42), images, boxes, crops, ocfg,
+                          cosine_weight=0.5)["loss"].item()
+    assert bs == 3 and abs(losses["loss_cosine"].item() - ref) <= 3e-3 * abs(ref)
+    g = student.visual.blocks[0].mlp.w3.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0

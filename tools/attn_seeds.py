@@ -1,0 +1,27 @@
+"""Worst-case errors of the attention forward over many random draws (guards the test tolerances)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from clipself_b200 import ops
+
+dev = torch.device("cuda:0")
+for (B, N, H) in [(2, 17, 2), (2, 65, 3), (3, 197, 12), (1, 577, 16)]:
+    D = H * 64
+    worst = [0.0, 0.0, 0.0, 0.0]
+    for seed in range(40):
+        torch.manual_seed(seed)
+        qkv = torch.randn(B * N, 3 * D, device=dev).to(torch.bfloat16)
+        out = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, N, device=dev)
+        stats = torch.full((B * N, 2 * H, 2), float("nan"), device=dev) if N <= 224 else None
+        ops.attention_fwd(qkv, B, N, H, 0.125, out, lse, stats)
+        q, k, v = (t.reshape(B, N, H, 64).permute(0, 2, 1, 3) for t in qkv.float().view(B, N, 3, D).unbind(2))
+        s = (q @ k.transpose(-1, -2)) * 0.125
+        ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+        worst[0] = max(worst[0], (out.float() - ref).abs().max().item())
+        worst[1] = max(worst[1], (lse - torch.logsumexp(s, -1)).abs().max().item())
+        if stats is not None:
+            o = ref.view(B * N, 2 * H, 32)
+            worst[2] = max(worst[2], (stats[..., 0] - o.sum(-1)).abs().max().item())
+            worst[3] = max(worst[3], (stats[..., 1] - (o * o).sum(-1)).abs().max().item())
+    print(f"B={B} N={N} H={H}: out {worst[0]:.3e}  lse {worst[1]:.3e}  s1 {worst[2]:.3e}  s2 {worst[3]:.3e}", flush=True)
