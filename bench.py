@@ -41,20 +41,28 @@ WORKLOADS = {
     # configs[4]: EVA ViT-L/14 336^2, 32 images per GPU (global 256 on 8 GPUs), 64 boxes/img + mask pooling of the
     # same dense map (the encode_masks arithmetic, eva_vit_model.py:645-653) every step
     "cfg5": dict(model="EVA02-CLIP-L-14-336", batch=32, boxes=64, kind="grid", mask_pool=True),
+    # the published recipe shape (scripts/train_clipself_coco_image_patches_eva_vitb16.sh): 2 images per GPU at
+    # --det-image-size 1024 (64x64 grid, 4097 tokens), 6x6 grid boxes, crops at 224
+    "recipe_b16": dict(model="EVA02-CLIP-B-16", batch=2, boxes=36, kind="grid", det=1024),
     # small variants for smoke / debugging
     "mini": dict(model="EVA02-CLIP-B-16", batch=8, boxes=8, kind="grid"),
 }
 
 
-def flops_per_image(cfg, K):
-    """F_step = K*F_teacher + 3*F_student_dense (2*M*N*K convention)."""
-    N, D, Hd, C, L = cfg.tokens, cfg.width, cfg.hidden, cfg.embed_dim, cfg.layers
-    pe = 2 * (N - 1) * (3 * cfg.patch ** 2) * D
-    blk = 8 * N * D * D + 4 * N * N * D + 6 * N * D * Hd
-    teacher = pe + L * blk + 2 * D * C
-    last = 4 * N * D * D + 6 * N * D * Hd
-    student = pe + (L - 1) * blk + last + 2 * (N - 1) * D * C
-    return K * teacher + 3 * student
+def flops_per_image(cfg, K, det=None):
+    """F_step = K*F_teacher + 3*F_student_dense (2*M*N*K convention); `det` = student
+    resolution when it differs from the tower's own."""
+    D, Hd, C, L = cfg.width, cfg.hidden, cfg.embed_dim, cfg.layers
+
+    def tower(N, dense):
+        pe = 2 * (N - 1) * (3 * cfg.patch ** 2) * D
+        blk = 8 * N * D * D + 4 * N * N * D + 6 * N * D * Hd
+        if not dense:
+            return pe + L * blk + 2 * D * C
+        return pe + (L - 1) * blk + 4 * N * D * D + 6 * N * D * Hd + 2 * (N - 1) * D * C
+
+    Ns = (det // cfg.patch) ** 2 + 1 if det else cfg.tokens
+    return K * tower(cfg.tokens, False) + 3 * tower(Ns, True)
 
 
 def sample_clocks_start(path):
@@ -113,10 +121,10 @@ def build_models(name, device):
     return student, teacher
 
 
-def synth_host_batch(cfg, B, K, kind, seed):
+def synth_host_batch(cfg, B, K, kind, seed, det=None):
     """Seeded synthetic batch with the reference's dataset contract (data.py:281), pinned host memory."""
     from clipself_b200.data import synthetic_batch
-    images, boxes, crops = synthetic_batch(cfg.image_size, B, K, kind, seed)
+    images, boxes, crops = synthetic_batch(det or cfg.image_size, B, K, kind, seed, crop_size=cfg.image_size)
     return images.pin_memory(), boxes.pin_memory(), crops.pin_memory()
 
 
@@ -141,7 +149,7 @@ def run_b200(args):
     B, K = wl["batch"], wl["boxes"]
     student, teacher = build_models(wl["model"], device)
     cfg = student.visual.cfg
-    host_batch = synth_host_batch(cfg, B, K, wl["kind"], seed=1234 + rank)
+    host_batch = synth_host_batch(cfg, B, K, wl["kind"], seed=1234 + rank, det=wl.get("det"))
     dev_batch = tuple(t.to(device) for t in host_batch)
     method = CLIPSelf()
     margs = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
@@ -250,13 +258,13 @@ def run_b200(args):
     value = world * B / (ms_step / 1e3)
     e2e_value = world * B / (e2e_ms / args.steps / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    step_tflops = value * flops_per_image(cfg, K) / 1e12
+    step_tflops = value * flops_per_image(cfg, K, wl.get("det")) / 1e12
     h2d = sum(t.numel() * t.element_size() for t in host_batch)
     out = {
-        "metric": f"images/sec ({K} boxes/img) {'ViT-B/16@224' if cfg.width == 768 else 'ViT-L/14@336'} distill step", "value": round(value, 2), "unit": "images/sec",
+        "metric": f"images/sec ({K} boxes/img) {('ViT-B/16@224' if cfg.width == 768 else 'ViT-L/14@336') + (f' student@{wl["det"]}' if wl.get('det') else '')} distill step", "value": round(value, 2), "unit": "images/sec",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['model']} {cfg.image_size}px student+teacher, per-GPU batch {B}, "
+        "config": {"workload": f"{args.workload}: {wl['model']} " + (f"student {wl['det']}px / teacher crops {cfg.image_size}px" if wl.get("det") else f"{cfg.image_size}px student+teacher") + f", per-GPU batch {B}, "
                                f"{K} {wl['kind']} boxes/img, full distill step fwd+bwd+AdamW, random init",
                    "global_batch": world * B, "boxes_per_image": K, "parallelism": f"dp{world}",
                    "l2_policy": f"inputs larger than L2 (crops {host_batch[2].numel() * 4 / 1e9:.2f} GB/step vs 126 MB L2), no explicit flush",

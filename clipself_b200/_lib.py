@@ -40,6 +40,7 @@ PROTOTYPES = {
     "cs_l2norm_fwd": [vp, i64, i32, vp, vp, vp],
     "cs_l2norm_bwd": [vp, vp, vp, i64, i32, vp, vp],
     "cs_im2col_patches": [vp, i32, i32, i32, i32, vp, i64, vp],
+    "cs_resize_bilinear": [vp, i32, i64, i32, i32, i32, i32, vp, vp],
     "cs_fill_cls_rows": [vp, vp, i32, i32, i32, vp, vp],
     "cs_layernorm_fwd": [vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, f32, vp, i64, vp, vp, vp],
     "cs_gemm_bf16": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],

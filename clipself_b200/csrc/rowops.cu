@@ -241,6 +241,37 @@ __global__ void pack_swiglu_kernel(const TIn* __restrict__ w1, const TIn* __rest
     if (threadIdx.x == 0 && bias12) bias12[prow] = ok ? (gate ? b1[src] : b2[src]) : 0.f;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// bilinear resize of image planes (align_corners = false, no antialiasing): the --multiscale student
+// input, training/clipself.py:17-27 (F.interpolate(images, size, mode='bilinear')).
+// Index arithmetic follows ATen's upsample_bilinear2d: scale = in/out (f32), src = scale*(dst+.5)-.5
+// clamped at 0, neighbour = +1 unless on the last row/column, weights (1-l, l).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void resize_bilinear_kernel(const T* __restrict__ src, int Hin, int Win, int Hout, int Wout,
+                                       float sy, float sx, T* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const long long plane = blockIdx.z;
+    if (x >= Wout) return;
+    float fy = fmaf(sy, (float)y + 0.5f, -0.5f);            // ATen's kernel is compiled with FMA contraction
+    float fx = fmaf(sx, (float)x + 0.5f, -0.5f);
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int yp = y0 < Hin - 1 ? 1 : 0, xp = x0 < Win - 1 ? 1 : 0;
+    const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const T* p = src + plane * Hin * Win + (long long)y0 * Win + x0;
+    const float v00 = (float)p[0], v01 = (float)p[xp];
+    const float v10 = (float)p[(long long)yp * Win], v11 = (float)p[(long long)yp * Win + xp];
+    const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+    const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+    const float val = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    dst[plane * Hout * Wout + (long long)y * Wout + x] = (T)val;
+}
+
 }  // namespace rowops
 }  // namespace cs
 
@@ -338,6 +369,24 @@ extern "C" int cs_im2col_patches(const void* images, cs_dtype_t dtype, int B, in
         im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)images, S, P, (__nv_bfloat16*)patches_bf16, ldp);
     else
         im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)images, S, P, (__nv_bfloat16*)patches_bf16, ldp);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+extern "C" int cs_resize_bilinear(const void* src, cs_dtype_t dtype, int64_t planes, int Hin, int Win, int Hout,
+                                  int Wout, void* dst, void* stream) {
+    CS_CHECK_ARG(src && dst, "cs_resize_bilinear: null pointer");
+    CS_CHECK_ARG(planes > 0 && planes < 65536 && Hin > 0 && Win > 0 && Hout > 0 && Hout < 65536 && Wout > 0,
+                 "cs_resize_bilinear: bad shape");
+    CS_CHECK_ARG(dtype == CS_F32 || dtype == CS_BF16, "cs_resize_bilinear: dtype must be f32 or bf16");
+    const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
+    dim3 grid(ceil_div(Wout, 128), Hout, (unsigned)planes);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CS_F32)
+        resize_bilinear_kernel<float><<<grid, 128, 0, st>>>((const float*)src, Hin, Win, Hout, Wout, sy, sx, (float*)dst);
+    else
+        resize_bilinear_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)src, Hin, Win, Hout, Wout, sy, sx,
+                                                                   (__nv_bfloat16*)dst);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

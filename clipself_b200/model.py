@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .student import StudentEngine
-from .tower import TowerCfg, TowerEngine, rope_tables
+from .tower import TowerCfg, TowerEngine, input_grid, rope_tables
 
 Tensor = torch.Tensor
 
@@ -271,14 +271,20 @@ class EVAVisionTransformer(nn.Module):
         eng.repack()
         return eng
 
-    def _infer_engine(self) -> TowerEngine:
+    def _infer_engine(self, x: Optional[Tensor] = None) -> TowerEngine:
+        """Forward-only engine; with `x` given, the view of it for x's resolution (any square multiple of
+        the patch size, like the reference tower: eva_vit_model.py:533-549, 631-643, rope.py:179-214)."""
+        eng = self._infer_engine_native()
+        return eng if x is None else eng.at_grid(input_grid(x, self.cfg))
+
+    def _infer_engine_native(self) -> TowerEngine:
         self._check_cuda()
         version = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
         if self._infer is None or version != self._infer_version:
             if self._infer is None:
                 self._infer = TowerEngine(self.cfg, self._tower_sd(), self._device())
             else:
-                self._infer.w.repack(self._tower_sd())
+                self._infer.repack(self._tower_sd())
             self._infer_version = version
         return self._infer
 
@@ -298,7 +304,8 @@ class EVAVisionTransformer(nn.Module):
         if self._needs_grad():
             raise NotImplementedError("gradient through the CLS path is not on the CLIPSelf hot path; "
                                       "call under torch.no_grad()")
-        return self._infer_engine().forward_cls(self._prep(x))
+        x = self._prep(x)
+        return self._infer_engine(x).forward_cls(x)
 
     def teacher_chunk_images(self) -> int:
         return self._infer_engine().chunk_images
@@ -320,7 +327,7 @@ class EVAVisionTransformer(nn.Module):
         if self._needs_grad():
             dense = _DenseFeatures.apply(self, x, *[p for _, p in self._block_params()])
         else:
-            dense = self._infer_engine().encode_dense_nograd(x)
+            dense = self._infer_engine(x).encode_dense_nograd(x)
         B, h, w, C = dense.shape
         return dense.permute(0, 3, 1, 2) if keep_shape else dense.reshape(B, h * w, C)
 
@@ -336,7 +343,7 @@ class EVAVisionTransformer(nn.Module):
         x = self._prep(x)
         if self._needs_grad():
             return _RoiFeatures.apply(self, x, rois, img_offsets, R, *[p for _, p in self._block_params()])
-        dense = self._infer_engine().encode_dense_nograd(x)
+        dense = self._infer_engine(x).encode_dense_nograd(x)
         return ops.roi_align_fwd(dense, rois, img_offsets, R)[0]
 
     def extract_roi_features(self, x: Tensor, normed_boxes: Sequence[Tensor], **kwargs) -> Tensor:

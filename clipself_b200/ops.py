@@ -139,6 +139,15 @@ def im2col_patches(images: Tensor, patch: int, ldp: int) -> Tensor:
     return out
 
 
+def resize_bilinear(images: Tensor, size: int) -> Tensor:
+    """F.interpolate(images, size=(size, size), mode='bilinear') for [B,C,H,W] f32 / bf16 (clipself.py:27)."""
+    _chk(images, None, "images")
+    B, Cc, H, W = images.shape
+    out = torch.empty(B, Cc, size, size, device=images.device, dtype=images.dtype)
+    call("cs_resize_bilinear", _p(images), _dt(images), B * Cc, H, W, size, size, _p(out), _stream())
+    return out
+
+
 def fill_cls_rows(cls_token: Tensor, pos_embed: Tensor, x: Tensor) -> None:
     B, N, D = x.shape
     call("cs_fill_cls_rows", _p(cls_token), _p(pos_embed), B, N, D, _p(x), _stream())

@@ -18,13 +18,14 @@ Memory layout (HBM, all f32, one allocation each for params / grads / Adam momen
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from . import _lib as L
 from . import ops
-from .tower import PackedTower, TowerCfg, _round_up
+from .tower import PackedTower, TowerCfg, _round_up, input_grid
 
 Tensor = torch.Tensor
 
@@ -113,8 +114,10 @@ class _BlockPack:
 class _Tape:
     """Saved activations of one student forward (allocated once per batch size)."""
 
-    def __init__(self, cfg: TowerCfg, B: int, dev):
-        D, Hd, N, H, Lr = cfg.width, cfg.hidden_pad, cfg.tokens, cfg.heads, cfg.layers   # Hd: padded hidden width
+    def __init__(self, cfg: TowerCfg, B: int, dev, grid: Optional[int] = None):
+        grid = grid or cfg.grid
+        D, Hd, N, H, Lr = cfg.width, cfg.hidden_pad, grid * grid + 1, cfg.heads, cfg.layers   # Hd: padded hidden width
+        self.grid, self.N = grid, N
         M = B * N
         Mp = B * (N - 1)
         bf = dict(device=dev, dtype=torch.bfloat16)
@@ -191,17 +194,14 @@ class StudentEngine:
         f = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
         fr = self.frozen
         from .tower import rope_tables, rope_vectors
-        cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
-        fr.rope_cos, fr.rope_sin = cos.to(dev), sin.to(dev)
-        pos, freq = rope_vectors(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
-        fr.rope_pos, fr.rope_freq = pos.to(dev), freq.to(dev)
+        self._res: Dict[int, SimpleNamespace] = {}
+        fr.pos_src = f("pos_embed")
         fr.k_pe = 3 * cfg.patch * cfg.patch
         fr.k_pe_pad = _round_up(fr.k_pe, 8)
         D = cfg.width
         fr.pe_w = ops.cast_pad_bf16(f("patch_embed.proj.weight").reshape(D, -1), fr.k_pe_pad)
         fr.pe_b = f("patch_embed.proj.bias")
         fr.cls = f("cls_token").reshape(-1)
-        fr.pos = f("pos_embed").reshape(cfg.tokens, D)
         fr.norm_g, fr.norm_b = f("norm.weight"), f("norm.bias")
         hw = f("head.weight")
         fr.head_w = torch.empty(cfg.embed_dim, D, device=dev, dtype=torch.bfloat16)
@@ -269,25 +269,45 @@ class StudentEngine:
             ops.cast_transpose(self.p(i, "mlp.w3.weight"), D, Hd, dst=pk.w3, dst_t=pk.w3T)
 
     # ------------------------------------------------------------------ forward
-    def tape(self, B: int) -> _Tape:
-        if self._tape is None or self._tape.B != B:
-            self._tape = _Tape(self.cfg, B, self.device)
+    def resolution(self, grid: int) -> SimpleNamespace:
+        """Per-resolution constants: RoPE tables / vectors with ft_seq_len = grid (rope.py:179-214) and the
+        bicubically rescaled pos_embed (eva_vit_model.py:631-643); the student runs at --det-image-size."""
+        r = self._res.get(grid)
+        if r is None:
+            from .tower import rescale_pos_embed, rope_tables, rope_vectors
+            cfg, dev = self.cfg, self.device
+            r = SimpleNamespace()
+            cos, sin = rope_tables(grid, cfg.head_dim, cfg.pt_seq_len)
+            r.rope_cos, r.rope_sin = cos.to(dev), sin.to(dev)
+            pos, freq = rope_vectors(grid, cfg.head_dim, cfg.pt_seq_len)
+            r.rope_pos, r.rope_freq = pos.to(dev), freq.to(dev)
+            r.pos = rescale_pos_embed(self.frozen.pos_src, grid)
+            self._res[grid] = r
+        return r
+
+    def tape(self, B: int, grid: Optional[int] = None) -> _Tape:
+        grid = grid or self.cfg.grid
+        if self._tape is None or self._tape.B != B or self._tape.grid != grid:
+            self._tape = None                       # release the old activations before allocating the new ones
+            self._tape = _Tape(self.cfg, B, self.device, grid)
         return self._tape
 
     def forward(self, images: Tensor) -> Tensor:
         """encode_dense with everything the backward needs kept on the tape.
         Returns the NHWC map [B,g,g,C] f32 (a view of the tape)."""
         cfg, fr = self.cfg, self.frozen
-        D, Hd, N = cfg.width, cfg.hidden, cfg.tokens
+        g = input_grid(images, cfg)
+        res = self.resolution(g)
+        D, Hd, N = cfg.width, cfg.hidden, g * g + 1
         B = images.shape[0]
-        t = self.tape(B)
+        t = self.tape(B, g)
         M = t.M
         eps = cfg.ln_eps
         # embed (frozen): same kernels as the teacher
         patches = ops.im2col_patches(images, cfg.patch, fr.k_pe_pad)
         ops.gemm(patches, fr.pe_w, t.x[0], M=B * (N - 1), N=D, K=fr.k_pe_pad, mode=L.EPI_TOKENS, bias=fr.pe_b,
-                 pos_embed=fr.pos, tokens=N)
-        ops.fill_cls_rows(fr.cls, fr.pos, t.x[0].view(B, N, D))
+                 pos_embed=res.pos, tokens=N)
+        ops.fill_cls_rows(fr.cls, res.pos, t.x[0].view(B, N, D))
         for i, pk in enumerate(self.packs):
             last = i == cfg.layers - 1
             st = t.stats[i]
@@ -295,7 +315,7 @@ class StudentEngine:
             ops.layernorm_fwd(x, M, D, self.p(i, "norm1.weight"), self.p(i, "norm1.bias"), eps, t.u[i], mean=st[0], rstd=st[1])
             if not last:
                 ops.gemm(t.u[i], pk.wqkv, t.qkv[i], M=M, mode=L.EPI_QKV_ROPE, bias=pk.bqkv,
-                         rope=(fr.rope_pos, fr.rope_freq), tokens=N, rope_cols=2 * D)
+                         rope=(res.rope_pos, res.rope_freq), tokens=N, rope_cols=2 * D)
                 ops.attention_fwd(t.qkv[i], B, N, cfg.heads, self.scale, t.att[i], t.lse[i])
             else:
                 ops.gemm(t.u[i], pk.wv, t.att[i], M=M, bias=self.p(i, "attn.v_bias"))
@@ -309,7 +329,6 @@ class StudentEngine:
             ops.layernorm_fwd(t.h[i], M, Hd, self.p(i, "mlp.ffn_ln.weight"), self.p(i, "mlp.ffn_ln.bias"), eps, t.hln[i],
                               mean=st[6], rstd=st[7])
             ops.gemm(t.hln[i], pk.w3, t.x[i + 1], M=M, bias=self.p(i, "mlp.w3.bias"), residual=t.xmid[i])
-        g = cfg.grid
         ops.layernorm_fwd(t.x[cfg.layers], t.Mp, D, fr.norm_g, fr.norm_b, eps, t.tok_ln, row_div=g * g, row_off=1,
                           mean=t.tok_stats[0], rstd=t.tok_stats[1])
         ops.gemm(t.tok_ln, fr.head_w, t.head, M=t.Mp, bias=fr.head_b)
@@ -322,9 +341,10 @@ class StudentEngine:
         """Gradient of the dense map w.r.t. every trainable block parameter, written into
         self.flat_grad[:n_grad] (overwritten, not accumulated: accum_freq == 1, train.py:89)."""
         cfg, fr, t = self.cfg, self.frozen, self._tape
-        D, Hd, N, H = cfg.width, cfg.hidden, cfg.tokens, cfg.heads
+        D, Hd, N, H = cfg.width, cfg.hidden, t.N, cfg.heads
         B, M, Mp = t.B, t.M, t.Mp
-        g2 = cfg.grid * cfg.grid
+        g2 = t.grid * t.grid
+        res = self.resolution(t.grid)
         ws = t.col_ws
         stream = torch.cuda.current_stream().cuda_stream
         # tail: normalise -> head -> final LN (all frozen: input gradients only)
@@ -385,7 +405,7 @@ class StudentEngine:
             ops.cast_transpose(t.u[i], M, D, dst_t=t.act_T_D)
             if not last:
                 ops.attention_bwd(t.qkv[i], t.att[i], d_att, t.lse[i], B, N, H, self.scale,
-                                  (fr.rope_cos, fr.rope_sin), t.delta, t.g_3D)                    # d_qkv (raw projections)
+                                  (res.rope_cos, res.rope_sin), t.delta, t.g_3D)                    # d_qkv (raw projections)
                 ops.cast_transpose(t.g_3D, M, 3 * D, dst_t=t.g_T_3D)
                 ops.gemm(t.g_T_3D, t.act_T_D, self._span(self.flat_grad, i, "attn.q_proj.weight", 3 * D, D),
                          M=3 * D, N=D, K=M, k_splits=-1)                                          # dWq|dWk|dWv

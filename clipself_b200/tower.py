@@ -16,6 +16,8 @@ All arithmetic runs in the CUDA library (clipself_b200/csrc); torch only owns th
 """
 from __future__ import annotations
 
+import copy
+import dataclasses
 import math
 import os
 from dataclasses import dataclass
@@ -62,6 +64,30 @@ class TowerCfg:
 
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+def input_grid(images: Tensor, cfg: "TowerCfg") -> int:
+    """Token grid of an input batch. Like the reference's towers (eva_vit_model.py:533-549) any square
+    resolution that is a multiple of the patch size is accepted; the grid is capped by the RoPE table the
+    QKV epilogue keeps in shared memory (64 x 64 = 1024 px at /16, 896 px at /14: the published recipes)."""
+    S = images.shape[-1]
+    if images.shape[-2] != S or S % cfg.patch != 0 or not 0 < S // cfg.patch <= 64:
+        raise ValueError(f"input must be square, a multiple of the patch size {cfg.patch} and at most "
+                         f"{64 * cfg.patch} px, got {tuple(images.shape[-2:])}")
+    return S // cfg.patch
+
+
+def rescale_pos_embed(pos_embed: Tensor, grid: int) -> Tensor:
+    """rescale_positional_embedding (eva_vit_model.py:631-643): the CLS row is kept, the [g0,g0] grid of
+    patch rows is resampled bicubically (align_corners=False) to [grid,grid]. -> [1 + grid^2, D] f32.
+    Parameter preprocessing, done once per resolution (pos_embed is frozen on this path)."""
+    pos = pos_embed.detach().reshape(-1, pos_embed.shape[-1]).float()
+    g0 = int(round(math.sqrt(pos.shape[0] - 1)))
+    if g0 == grid:
+        return pos.contiguous()
+    pe = pos[1:].T.contiguous().view(1, -1, g0, g0)
+    pe = torch.nn.functional.interpolate(pe, (grid, grid), mode="bicubic", align_corners=False).view(-1, grid * grid)
+    return torch.cat([pos[:1], pe.T], dim=0).contiguous()
 
 
 def rope_tables(grid: int, head_dim: int, pt_seq_len: int, theta: float = 10000.0):
@@ -122,7 +148,8 @@ class PackedTower:
         self.pe_w = ops.cast_pad_bf16(f("patch_embed.proj.weight").reshape(D, -1), self.k_pe_pad)
         self.pe_b = f("patch_embed.proj.bias")
         self.cls = f("cls_token").reshape(-1)
-        self.pos = f("pos_embed").reshape(cfg.tokens, D)
+        self.pos_src = f("pos_embed")
+        self.pos = rescale_pos_embed(self.pos_src, cfg.grid)
         self.norm_g, self.norm_b = f("norm.weight"), f("norm.bias")
         self.head_w = ops.cast_pad_bf16(f("head.weight"))
         self.head_b = f("head.bias")
@@ -189,6 +216,37 @@ class TowerEngine:
         # and an even number of SwiGLU tiles per row
         self.fold_proj = cfg.tokens <= 224 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
         self.fold_w3 = (cfg.hidden_pad // 128) % 2 == 0 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+
+        self._views: Dict[int, "TowerEngine"] = {}
+
+    def repack(self, sd: Dict[str, Tensor]) -> None:
+        self.w.repack(sd)
+        self._views.clear()
+
+    def at_grid(self, grid: int) -> "TowerEngine":
+        """The same tower at another input resolution (token grid): shares the packed block weights,
+        owns its RoPE vectors, rescaled pos_embed and workspace (rope.py:179-214, eva_vit_model.py:631-643)."""
+        if grid == self.cfg.grid:
+            return self
+        v = self._views.get(grid)
+        if v is None:
+            cfg = dataclasses.replace(self.cfg, image_size=grid * self.cfg.patch)
+            v = TowerEngine.__new__(TowerEngine)
+            v.cfg, v.device, v.scale = cfg, self.device, self.scale
+            v.w = copy.copy(self.w)
+            v.w.cfg = cfg
+            cos, sin = rope_tables(grid, cfg.head_dim, cfg.pt_seq_len)
+            v.w.rope_cos, v.w.rope_sin = cos.to(self.device), sin.to(self.device)
+            pos, freq = rope_vectors(grid, cfg.head_dim, cfg.pt_seq_len)
+            v.w.rope_pos, v.w.rope_freq = pos.to(self.device), freq.to(self.device)
+            v.w.pos = rescale_pos_embed(self.w.pos_src, grid)
+            v.chunk_images = max(1, self.chunk_images * self.cfg.tokens // cfg.tokens)
+            v._ws = None
+            v.fold_proj = cfg.tokens <= 224 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+            v.fold_w3 = self.fold_w3
+            v._views = {}
+            self._views[grid] = v
+        return v
 
     # ------------------------------------------------------------------ helpers
     def workspace(self, images: int) -> Workspace:

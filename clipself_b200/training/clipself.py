@@ -104,8 +104,8 @@ class CLIPSelf:
             else:
                 raise NotImplementedError
             tar_size = random.choice(tar_sizes)
-            raise NotImplementedError(f"--multiscale (student at {tar_size}px) needs the variable-resolution "
-                                      "tower: SURVEY.md §8f rank 4, not built yet")
+            if tar_size != cur_h:
+                images = ops.resize_bilinear(images.contiguous(), tar_size)
 
         # student forward first: it only needs the (small) images, so it overlaps the crop H2D stream
         model.visual.sync_gradients = bool(distributed)

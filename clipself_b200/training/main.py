@@ -80,8 +80,9 @@ def main(argv=None):
     dist_model.eval()
     method = CLIPSelf()
 
-    dataset = SyntheticDistillDataset(args.det_image_size if args.det_image_size <= model.visual.image_size
-                                      else model.visual.image_size, args.input_size, args.max_boxes,
+    # student images at --det-image-size (scripts: 1024 / 896), teacher crops at the tower's own size
+    # (data.py:226-245: crops are resized to args.input_size)
+    dataset = SyntheticDistillDataset(args.det_image_size, args.input_size, args.max_boxes,
                                       kind="grid", length=max(args.batch_size * world * 8, 64), seed=args.seed)
     sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, seed=args.seed) \
         if args.distributed else None

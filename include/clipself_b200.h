@@ -105,6 +105,12 @@ int cs_l2norm_bwd(const float* y, const float* inv_norm, const float* d_y, int64
 int cs_im2col_patches(const void* images, cs_dtype_t dtype, int B, int S, int P,
                       void* patches_bf16, int64_t ldp, void* stream);
 
+/* Bilinear resize of `planes` image planes [Hin,Win] -> [Hout,Wout] (f32 or bf16, same dtype out),
+ * align_corners = false, no antialiasing: the --multiscale student input
+ * (training/clipself.py:17-27, F.interpolate(images, size=(t,t), mode='bilinear')). */
+int cs_resize_bilinear(const void* src, cs_dtype_t dtype, int64_t planes, int Hin, int Win, int Hout, int Wout,
+                       void* dst, void* stream);
+
 /* x[b,0,:] = cls_token + pos_embed[0]  (eva_vit_model.py:540-543); x [B,N,D] f32. */
 int cs_fill_cls_rows(const float* cls_token, const float* pos_embed, int B, int N, int D, float* x,
                      void* stream);

@@ -108,7 +108,25 @@ def embed_tokens(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg) -> Tensor
     x = x.flatten(2).transpose(1, 2)
     cls = sd["cls_token"].expand(x.shape[0], -1, -1)
     x = torch.cat([cls, x], dim=1)
-    return x + sd["pos_embed"]
+    return x + rescale_pos_embed(sd["pos_embed"], images.shape[-1] // cfg.patch)
+
+
+def rescale_pos_embed(pos_embed: Tensor, grid: int) -> Tensor:
+    """E:631-643 (rescale_positional_embedding): unchanged at the pretraining grid; otherwise the CLS
+    row is kept and the [g0,g0] grid of patch rows is resampled bicubically (align_corners=False)."""
+    g0 = int(round((pos_embed.shape[1] - 1) ** 0.5))
+    if g0 == grid:
+        return pos_embed
+    pe = pos_embed[0, 1:].T.contiguous().view(1, -1, g0, g0)
+    pe = F.interpolate(pe, (grid, grid), mode="bicubic", align_corners=False).view(-1, grid * grid)
+    return torch.cat([pos_embed[0, :1], pe.T.contiguous()], dim=0)[None]
+
+
+def image_grid(images: Tensor, cfg: TowerCfg) -> int:
+    """Token grid of a (square) input: the reference's towers accept any resolution — RoPE tables are
+    regenerated with ft_seq_len = grid (rope.py:179-214) and pos_embed is rescaled (E:631-643)."""
+    assert images.shape[-1] == images.shape[-2] and images.shape[-1] % cfg.patch == 0
+    return images.shape[-1] // cfg.patch
 
 
 def swiglu(x: Tensor, sd: Dict[str, Tensor], p: str, eps: float) -> Tensor:
@@ -162,7 +180,7 @@ def block(x: Tensor, sd: Dict[str, Tensor], i: int, cfg: TowerCfg, cos: Tensor, 
 def tower_forward_cls(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg,
                       taps: Dict[str, Tensor] | None = None) -> Tensor:
     """Teacher path: all blocks, final LN, CLS row, head (E:533-570, E:581-586)."""
-    cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
+    cos, sin = rope_tables(image_grid(images, cfg), cfg.head_dim, cfg.pt_seq_len)
     x = embed_tokens(sd, images, cfg)
     if taps is not None:
         taps["tokens0"] = x
@@ -177,7 +195,8 @@ def tower_forward_cls(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg,
 def tower_encode_dense(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg,
                        taps: Dict[str, Tensor] | None = None) -> Tensor:
     """Student dense map, NHWC [B,h,w,C], unit-norm per token (E:588-623)."""
-    cos, sin = rope_tables(cfg.grid, cfg.head_dim, cfg.pt_seq_len)
+    g = image_grid(images, cfg)
+    cos, sin = rope_tables(g, cfg.head_dim, cfg.pt_seq_len)
     x = embed_tokens(sd, images, cfg)
     for i in range(cfg.layers - 1):
         x = block(x, sd, i, cfg, cos, sin)
@@ -187,7 +206,7 @@ def tower_encode_dense(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg,
     x = _ln(x, sd, "norm", cfg.ln_eps)
     x = F.linear(x, sd["head.weight"], sd["head.bias"])
     x = F.normalize(x, dim=-1)
-    return x.reshape(images.shape[0], cfg.grid, cfg.grid, -1)
+    return x.reshape(images.shape[0], g, g, -1)
 
 
 # --------------------------------------------------------------------------------------
@@ -308,7 +327,7 @@ def clipself_step(student_sd: Dict[str, Tensor], teacher_sd: Dict[str, Tensor],
     with torch.no_grad():
         teacher = tower_forward_cls(teacher_sd, crops, cfg)
     dense = tower_encode_dense(student_sd, images, cfg)
-    boxes = denormalize_boxes(rois, cfg.grid, cfg.grid)
+    boxes = denormalize_boxes(rois, dense.shape[1], dense.shape[2])
     student = roi_align_1x1_nhwc(dense, boxes)
     loss = cosine_loss(student, teacher, cosine_weight)
     return dict(loss=loss, student_roi=student, teacher=teacher, dense=dense,
@@ -381,8 +400,8 @@ def grid_box_templates(m: int, n: int) -> Tensor:
 
 
 def synth_batch(cfg: TowerCfg, batch: int, boxes_per_image: int, seed: int,
-                kind: str = "grid", ragged: bool = False, crop_size: int | None = None
-                ) -> Tuple[Tensor, Tensor, Tensor]:
+                kind: str = "grid", ragged: bool = False, crop_size: int | None = None,
+                det_size: int | None = None) -> Tuple[Tensor, Tensor, Tensor]:
     """(images [B,3,S,S], normed_boxes [B,K,5], image_crops [B,K,3,s,s]) as the reference's
     datasets emit them (training/data.py:281), from a seeded numpy PCG64 stream.
 
@@ -391,7 +410,7 @@ def synth_batch(cfg: TowerCfg, batch: int, boxes_per_image: int, seed: int,
     ragged=True zeroes a random tail of each image's rows (valid flag 0, data.py:265,276-277)."""
     import numpy as np
     rng = np.random.Generator(np.random.PCG64(seed))
-    S = cfg.image_size
+    S = det_size or cfg.image_size          # student (detector-resolution) image size, --det-image-size
     s = crop_size or cfg.image_size
     K = boxes_per_image
     images = torch.from_numpy(rng.standard_normal((batch, 3, S, S), dtype=np.float32))

@@ -55,13 +55,13 @@ def build_reference_model(cfg: O.TowerCfg, seed: int, name: str | None):
 
 
 def run_case(tag, cfg, name, batch, K, kind, ragged, seed, store_inputs, store_all_grads, tap_blocks=None,
-             backward=True):
+             backward=True, det_size=None):
     student = build_reference_model(cfg, seed, name)
     teacher = build_reference_model(cfg, seed + 1, name)
     student.lock_image_tower(unlocked_groups=cfg.layers)      # main.py:161-166
     student.train()
     teacher.eval()
-    images, boxes, crops = O.synth_batch(cfg, batch, K, seed + 2, kind=kind, ragged=ragged)
+    images, boxes, crops = O.synth_batch(cfg, batch, K, seed + 2, kind=kind, ragged=ragged, det_size=det_size)
     args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
 
     taps = {}
@@ -92,7 +92,7 @@ def run_case(tag, cfg, name, batch, K, kind, ragged, seed, store_inputs, store_a
         dense = student.encode_dense(images, normalize=False, keep_shape=True)      # NCHW view
         out["dense_nhwc"] = dense.permute(0, 2, 3, 1).contiguous().numpy()
         # masks: the boxes rasterised at feature resolution
-        g = cfg.grid
+        g = (det_size or cfg.image_size) // cfg.patch
         masks = []
         for r in rois:
             m = torch.zeros(r.shape[0], g, g)
@@ -139,6 +139,10 @@ if __name__ == "__main__":
              store_inputs=True, store_all_grads=True)
     run_case("tiny_grid", O.CFG_TINY, None, batch=2, K=4, kind="grid", ragged=False, seed=200,
              store_inputs=True, store_all_grads=False)
+    # student at a detector resolution != the tower's own (scripts: --det-image-size 1024): 160 px -> 10x10 grid
+    # on the 4x4-pretrained tiny tower; exercises the RoPE regeneration and the bicubic pos_embed rescale
+    run_case("tiny_multires", O.CFG_TINY, None, batch=2, K=4, kind="proposal", ragged=True, seed=500,
+             store_inputs=True, store_all_grads=True, det_size=160)
     # BASELINE.json configs[0]: ViT-B/16, 2x224x224, 8 patch-boxes/img
     run_case("cfg1_b16", O.CFG_B16, "EVA02-CLIP-B-16", batch=2, K=8, kind="grid", ragged=False, seed=300,
              store_inputs=False, store_all_grads=False, tap_blocks=(0, 10))

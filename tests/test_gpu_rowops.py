@@ -83,3 +83,21 @@ def test_attention_fwd(dev, B, N, H):
         o = ref.view(B * N, 2 * H, 32)
         torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-2, atol=5e-2)
         torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("hin,hout", [(1024, 320), (896, 672), (64, 160), (224, 224), (37, 53)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_resize_bilinear(dev, hin, hout, dtype):
+    """--multiscale input resize (clipself.py:27) against torch's own bilinear interpolate."""
+    from clipself_b200 import ops
+    torch.manual_seed(hin + hout)
+    x = torch.randn(2, 3, hin, hin, device=dev).to(dtype)
+    y = ops.resize_bilinear(x, hout)
+    ref = torch.nn.functional.interpolate(x.float(), size=(hout, hout), mode="bilinear").to(dtype)
+    assert y.shape == ref.shape and y.dtype == dtype
+    if dtype == torch.float32:
+        torch.testing.assert_close(y, ref, rtol=0, atol=1e-5)          # same index math; FMA contraction only
+    else:
+        torch.testing.assert_close(y.float(), ref.float(), rtol=8e-3, atol=1e-6)   # 1 bf16 ulp
+    if hin == hout:
+        assert torch.equal(y, x)

@@ -11,7 +11,9 @@ from oracle import clipself_oracle as O
 pytestmark = pytest.mark.gpu
 
 CASES = {"tiny_ragged": (O.CFG_TINY, 3, 5, "proposal", True), "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
-         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False), "l14_fwd": (O.CFG_L14_336, 1, 2, "proposal", False)}
+         "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False), "l14_fwd": (O.CFG_L14_336, 1, 2, "proposal", False),
+         "tiny_multires": (O.CFG_TINY, 2, 4, "proposal", True)}
+DET_SIZE = {"tiny_multires": 160}      # student images at a detector resolution != the tower's own (10x10 grid)
 
 
 def build_model(ocfg, seed, dev):
@@ -30,7 +32,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("tag,host_batch", [("tiny_ragged", True), ("tiny_ragged", False), ("tiny_grid", True),
-                                            ("cfg1_b16", True), ("l14_fwd", True)])
+                                            ("cfg1_b16", True), ("l14_fwd", True), ("tiny_multires", True)])
 def test_step_vs_golden(golden, tag, host_batch):
     from clipself_b200.training.clipself import CLIPSelf
     ocfg, B, K, kind, ragged = CASES[tag]
@@ -42,7 +44,7 @@ def test_step_vs_golden(golden, tag, host_batch):
     student.lock_image_tower(unlocked_groups=ocfg.layers)
     student.train()
     teacher.eval()
-    batch = O.synth_batch(ocfg, B, K, seed + 2, kind=kind, ragged=ragged)
+    batch = O.synth_batch(ocfg, B, K, seed + 2, kind=kind, ragged=ragged, det_size=DET_SIZE.get(tag))
     if not host_batch:
         batch = tuple(t.to(dev) for t in batch)
     args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
@@ -141,3 +143,95 @@ def test_step_with_an_image_without_boxes():
     assert bs == 3 and abs(losses["loss_cosine"].item() - ref) <= 3e-3 * abs(ref)
     g = student.visual.blocks[0].mlp.w3.weight.grad
     assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+def test_multires_inference_vs_golden(golden):
+    """encode_dense / encode_pseudo_boxes / encode_masks / encode_image at a resolution other than the
+    tower's own (RoPE regeneration rope.py:179-214, bicubic pos_embed eva_vit_model.py:631-643)."""
+    g = golden("tiny_multires")
+    ocfg, B, K, kind, ragged = CASES["tiny_multires"]
+    dev = torch.device("cuda")
+    m = build_model(ocfg, int(g["seed"]), dev).eval()
+    images, boxes, _ = O.synth_batch(ocfg, B, K, int(g["seed"]) + 2, kind=kind, ragged=ragged, det_size=160)
+    rois = [b[b[:, -1] > 0.5, :4].to(dev) for b in boxes]
+    with torch.no_grad():
+        d = m.encode_dense(images.to(dev), normalize=False, keep_shape=True)
+        f = m.encode_pseudo_boxes(images.to(dev), rois, normalize=True)
+        masks = [t.to(dev) for t in torch.split(torch.from_numpy(g["masks"]), [r.shape[0] for r in rois])]
+        mp = m.encode_masks(images.to(dev), masks, normalize=True)
+        cls = m.encode_image(images.to(dev), normalize=False)
+        native = m.encode_dense(images[:, :, :64, :64].contiguous().to(dev), keep_shape=True)   # back to 4x4
+    assert d.shape == (B, ocfg.embed_dim, 10, 10) and native.shape == (B, ocfg.embed_dim, 4, 4)
+    assert rel(d.permute(0, 2, 3, 1).cpu().numpy(), g["dense_nhwc"]) < 1.5e-2
+    assert rel(f.cpu().numpy(), g["student_roi_normalized"]) < 1.5e-2
+    assert rel(mp.cpu().numpy(), g["mask_pooled"]) < 1.5e-2
+    ref_cls = O.tower_forward_cls(O.synth_tower_weights(ocfg, int(g["seed"])), images, ocfg)
+    assert rel(cls.cpu().numpy(), ref_cls.numpy()) < 1.5e-2
+    with pytest.raises(ValueError):
+        m.encode_dense(torch.zeros(1, 3, 72, 72, device=dev))          # not a multiple of the patch size
+
+
+def test_b16_student_at_448_vs_oracle():
+    """EVA02-B/16 student at 448 px (28x28 grid, 785 tokens: the long-sequence attention kernels) against the
+    oracle: loss and a sample of gradients."""
+    from clipself_b200.training.clipself import CLIPSelf
+    ocfg = O.CFG_B16
+    dev = torch.device("cuda")
+    student, teacher = build_model(ocfg, 71, dev), build_model(ocfg, 72, dev)
+    student.lock_image_tower(unlocked_groups=ocfg.layers)
+    student.train()
+    teacher.eval()
+    batch = O.synth_batch(ocfg, 1, 3, 73, kind="proposal", det_size=448)
+    args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+    losses, _, _ = CLIPSelf()(batch, student, teacher, None, dev, None, False, args)
+    losses["loss_cosine"].backward()
+    torch.cuda.synchronize()
+    ssd, tsd = O.synth_tower_weights(ocfg, 71), O.synth_tower_weights(ocfg, 72)
+    watch = ["blocks.0.attn.q_proj.weight", "blocks.5.attn.proj.weight", "blocks.11.mlp.w3.weight", "blocks.3.norm1.weight"]
+    for k in watch:
+        ssd[k].requires_grad_(True)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    out = O.clipself_step(ssd, tsd, *batch, ocfg)
+    out["loss"].backward()
+    print(f"b16@448: loss {losses['loss_cosine'].item():.6f} oracle {out['loss'].item():.6f}")
+    assert abs(losses["loss_cosine"].item() - out["loss"].item()) <= 1e-3 * abs(out["loss"].item())
+    params = dict(student.visual.named_parameters())
+    for k in watch:
+        r = rel(params[k].grad.cpu().numpy(), ssd[k].grad.numpy())
+        print(f"  {k}: rel-L2 {r:.3e}")
+        assert r <= 0.08, (k, r)
+
+
+@pytest.mark.parametrize("want", [1024, 640])
+def test_multiscale_step_vs_oracle(want):
+    """args.multiscale (clipself.py:17-27): 1024 px student images, target size drawn with random.choice;
+    1024 keeps the full 64x64 grid (4097 tokens), 640 goes through the bilinear resize kernel."""
+    import random
+    from clipself_b200.training.clipself import CLIPSelf
+    ocfg = O.CFG_TINY
+    dev = torch.device("cuda")
+    student, teacher = build_model(ocfg, 81, dev), build_model(ocfg, 82, dev)
+    student.lock_image_tower(unlocked_groups=ocfg.layers)
+    student.train()
+    teacher.eval()
+    seed = next(s for s in range(100) if random.Random(s).choice([320, 640, 896, 1024]) == want)
+    batch = O.synth_batch(ocfg, 1, 3, 83, kind="proposal", det_size=1024)
+    args = types.SimpleNamespace(multiscale=True, extract_type="v2", cosine_weight=1.0)
+    random.seed(seed)
+    losses, _, _ = CLIPSelf()(batch, student, teacher, None, dev, None, False, args)
+    losses["loss_cosine"].backward()
+    torch.cuda.synchronize()
+    ssd, tsd = O.synth_tower_weights(ocfg, 81), O.synth_tower_weights(ocfg, 82)
+    watch = ["blocks.0.attn.q_proj.weight", "blocks.1.attn.v_proj.weight", "blocks.2.mlp.w3.weight", "blocks.1.norm2.bias"]
+    for k in watch:
+        ssd[k].requires_grad_(True)
+    images = torch.nn.functional.interpolate(batch[0], size=(want, want), mode="bilinear")
+    out = O.clipself_step(ssd, tsd, images, batch[1], batch[2], ocfg)
+    out["loss"].backward()
+    print(f"multiscale {want}: loss {losses['loss_cosine'].item():.6f} oracle {out['loss'].item():.6f}")
+    assert abs(losses["loss_cosine"].item() - out["loss"].item()) <= 1e-3 * abs(out["loss"].item())
+    params = dict(student.visual.named_parameters())
+    for k in watch:
+        r = rel(params[k].grad.cpu().numpy(), ssd[k].grad.numpy())
+        print(f"  {k}: rel-L2 {r:.3e}")
+        assert r <= 0.08, (k, r)

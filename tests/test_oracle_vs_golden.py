@@ -12,14 +12,16 @@ CASES = {
     "tiny_grid": (O.CFG_TINY, 2, 4, "grid", False),
     "cfg1_b16": (O.CFG_B16, 2, 8, "grid", False),
     "l14_fwd": (O.CFG_L14_336, 1, 2, "proposal", False),
+    "tiny_multires": (O.CFG_TINY, 2, 4, "proposal", True),      # student images at 160 px (10x10 grid)
 }
+DET_SIZE = {"tiny_multires": 160}
 
 
 def _run(golden, tag, need_grad):
     cfg, B, K, kind, ragged = CASES[tag]
     g = golden(tag)
     seed = int(g["seed"])
-    images, boxes, crops = O.synth_batch(cfg, B, K, seed + 2, kind=kind, ragged=ragged)
+    images, boxes, crops = O.synth_batch(cfg, B, K, seed + 2, kind=kind, ragged=ragged, det_size=DET_SIZE.get(tag))
     assert np.array_equal(boxes.numpy(), g["boxes"])                    # bit-exact boxes
     if "images" in g.files:
         assert np.array_equal(images.numpy(), g["images"])
@@ -37,7 +39,7 @@ def _run(golden, tag, need_grad):
     return g, out, ssd
 
 
-@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_grid"])
+@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_grid", "tiny_multires"])
 def test_forward_tiny(golden, tag):
     g, out, _ = _run(golden, tag, need_grad=False)
     np.testing.assert_allclose(out["teacher"].numpy(), g["teacher"], rtol=1e-4, atol=2e-5)
@@ -46,8 +48,9 @@ def test_forward_tiny(golden, tag):
     np.testing.assert_allclose(out["loss"].item(), float(g["loss"]), rtol=1e-5)
 
 
-def test_backward_tiny(golden):
-    g, out, ssd = _run(golden, "tiny_ragged", need_grad=True)
+@pytest.mark.parametrize("tag", ["tiny_ragged", "tiny_multires"])
+def test_backward_tiny(golden, tag):
+    g, out, ssd = _run(golden, tag, need_grad=True)
     out["loss"].backward()
     names = [str(n) for n in g["grad_names"]]
     for name, norm in zip(names, g["grad_norms"]):
