@@ -228,6 +228,15 @@ def run_b200(args):
     for _ in range(2):
         step(host_batch)
     e2e_ms, _ = timed(host_batch, args.steps, read_loss=True)
+    # context for the e2e number: the raw pinned-host -> HBM copy rate of this box for one step's crops
+    crops_dev = method._crops_dev if getattr(method, "_crops_dev", None) is not None else torch.empty_like(host_batch[2], device=device)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    crops_dev.view(-1)[:host_batch[2].numel()].copy_(host_batch[2].view(-1), non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = host_batch[2].numel() * 4 / c0.elapsed_time(c1) / 1e6
 
     # roofline of the dominant kernel: event-time every GEMM launch of one more step
     ops.GEMM_PROFILE = []
@@ -270,7 +279,8 @@ def run_b200(args):
                    "l2_policy": f"inputs larger than L2 (crops {host_batch[2].numel() * 4 / 1e9:.2f} GB/step vs 126 MB L2), no explicit flush",
                    "step_tflops": round(step_tflops, 1), "step_frac_of_peak": round(step_tflops / (world * peak_tf), 4),
                    "last_loss": float(last_loss.detach())},
-        "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_copy_alone_gbs": round(h2d_gbs, 1)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "cs::gemm::gemm_kernel (tcgen05)", "achieved": round(achieved, 1),

@@ -89,33 +89,52 @@ __device__ __forceinline__ void axis_weights(float lo_n, float hi_n, int size, f
     *count_out = grid;
 }
 
-__global__ void roi_weights_kernel(const float* __restrict__ rois, int R, int H, int W, float* __restrict__ wy,
-                                   float* __restrict__ wx) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const float* b = rois + (long long)r * 4;
-    int gw, gh;
-    axis_weights(b[0], b[2], W, wx + (long long)r * W, &gw);
-    axis_weights(b[1], b[3], H, wy + (long long)r * H, &gh);
-    const float count = (float)max(gw * gh, 1);
-    const float inv = 1.0f / count;
-    for (int i = 0; i < H; ++i) wy[(long long)r * H + i] *= inv;
+// 32 boxes per CTA, one thread per box; the weight rows are accumulated in shared memory (the scatter
+// `w[lo] += h` is a read-modify-write chain) and written back coalesced: the CTA's rows are contiguous.
+constexpr int RW_BOXES = 32;
+__global__ void __launch_bounds__(RW_BOXES)
+roi_weights_kernel(const float* __restrict__ rois, int R, int H, int W, float* __restrict__ wy,
+                   float* __restrict__ wx) {
+    extern __shared__ float s_w[];                   // [RW_BOXES][W] then [RW_BOXES][H]
+    float* s_wx = s_w;
+    float* s_wy = s_w + RW_BOXES * W;
+    const int r0 = blockIdx.x * RW_BOXES;
+    const int r = r0 + threadIdx.x;
+    const int n = min(RW_BOXES, R - r0);
+    if (r < R) {
+        const float4 b = *reinterpret_cast<const float4*>(rois + (long long)r * 4);
+        int gw, gh;
+        float* mx = s_wx + threadIdx.x * W;
+        float* my = s_wy + threadIdx.x * H;
+        axis_weights(b.x, b.z, W, mx, &gw);
+        axis_weights(b.y, b.w, H, my, &gh);
+        const float count = (float)max(gw * gh, 1);
+        const float inv = 1.0f / count;
+        for (int i = 0; i < H; ++i) my[i] *= inv;
+    }
+    __syncwarp();
+    for (int i = threadIdx.x; i < n * W; i += RW_BOXES) wx[(long long)r0 * W + i] = s_wx[i];
+    for (int i = threadIdx.x; i < n * H; i += RW_BOXES) wy[(long long)r0 * H + i] = s_wy[i];
 }
 
 constexpr int ROI_CS = 64;       // channel slice per CTA
-constexpr int ROI_LANES = 4;     // roi (or pixel) lanes per CTA
+constexpr int ROI_LANES = 8;     // roi (or pixel) lanes per CTA (each lane = two warps of 32 channels)
 constexpr int ROI_THREADS = ROI_CS * ROI_LANES;
 constexpr int ROI_CHUNK = 64;    // rois whose separable weights are staged in shared memory at once
 
-// first / last index with a non-zero weight (the support of a box along one axis is contiguous)
+// first / last index with a non-zero weight (the support of a box along one axis is contiguous).
+// Warp-cooperative: the 32 threads of a warp always work on the same box (they are 32 channels of it).
 __device__ __forceinline__ void support(const float* __restrict__ w, int n, int& lo, int& hi) {
+    const int l = threadIdx.x & 31;
     lo = n;
     hi = -1;
-    for (int i = 0; i < n; ++i)
-        if (w[i] != 0.f) {
-            if (lo == n) lo = i;
-            hi = i;
+    for (int base = 0; base < n; base += 32) {
+        const unsigned m = __ballot_sync(0xffffffffu, base + l < n && w[base + l] != 0.f);
+        if (m) {
+            if (lo == n) lo = base + __ffs(m) - 1;
+            hi = base + 31 - __clz(m);
         }
+    }
 }
 
 // out[r, c] = sum_{y,x} wy[r,y] wx[r,x] f[b,y,x,c];  grid (C/64, B).
@@ -242,7 +261,7 @@ roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const
 // Pixel chunks of the map slice and of the image's masks are staged in shared memory; every thread keeps
 // the accumulators of its boxes (one channel, every 4th box) in registers.
 constexpr int MP_PX = 64;        // pixels per staged chunk
-constexpr int MP_ACC = 16;       // boxes per thread per pass (x 4 lanes = 64 boxes per pass)
+constexpr int MP_ACC = 8;        // boxes per thread per pass (x 8 lanes = 64 boxes per pass)
 __global__ void __launch_bounds__(ROI_THREADS)
 mask_pool_kernel(const float* __restrict__ fmap, int HW, int C, const float* __restrict__ masks,
                  const int* __restrict__ img_offsets, float* __restrict__ out) {
@@ -445,11 +464,12 @@ extern "C" int cs_roi_align_fwd(const float* fmap, int B, int H, int W, int C, c
                                 const int32_t* img_offsets, int R, float* wy, float* wx, float* out,
                                 void* stream) {
     CS_CHECK_ARG(fmap && rois && img_offsets && wy && wx && out, "cs_roi_align_fwd: null pointer");
-    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 512, "cs_roi_align_fwd: bad shape");
-    CS_CHECK_ARG((uintptr_t)fmap % 16 == 0 && C % 4 == 0, "cs_roi_align_fwd: fmap must be 16 B aligned, C %% 4 == 0");
+    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 384, "cs_roi_align_fwd: bad shape");
+    CS_CHECK_ARG((uintptr_t)fmap % 16 == 0 && (uintptr_t)rois % 16 == 0 && C % 4 == 0,
+                 "cs_roi_align_fwd: fmap and rois must be 16 B aligned, C %% 4 == 0");
     if (R == 0) return CS_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    roi_weights_kernel<<<ceil_div(R, 128), 128, 0, st>>>(rois, R, H, W, wy, wx);
+    roi_weights_kernel<<<ceil_div(R, RW_BOXES), RW_BOXES, RW_BOXES * (H + W) * sizeof(float), st>>>(rois, R, H, W, wy, wx);
     CS_LAUNCH_CHECK();
     dim3 grid(ceil_div(C, ROI_CS), B);
     const bool stage = roi_smem_bytes(H, W, true) <= kMaxStage;
@@ -469,7 +489,7 @@ extern "C" int cs_roi_align_fwd(const float* fmap, int B, int H, int W, int C, c
 extern "C" int cs_roi_align_bwd(const float* d_out, int B, int H, int W, int C, const int32_t* img_offsets,
                                 int R, const float* wy, const float* wx, float* d_fmap, void* stream) {
     CS_CHECK_ARG(d_out && img_offsets && wy && wx && d_fmap, "cs_roi_align_bwd: null pointer");
-    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 512, "cs_roi_align_bwd: bad shape");
+    CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 384, "cs_roi_align_bwd: bad shape");
     CS_CHECK_ARG((uintptr_t)d_fmap % 16 == 0 && C % 4 == 0, "cs_roi_align_bwd: d_fmap must be 16 B aligned, C %% 4 == 0");
     dim3 grid(ceil_div(C, ROI_CS), B);
     const bool stage = roi_smem_bytes(H, W, true) <= kMaxStage;

@@ -307,12 +307,14 @@ class EVAVisionTransformer(nn.Module):
         x = self._prep(x)
         return self._infer_engine(x).forward_cls(x)
 
-    def teacher_chunk_images(self) -> int:
-        return self._infer_engine().chunk_images
+    def teacher_chunk_schedule(self, R: int):
+        """(start, count) pieces in which forward_chunked() walks R crops (one H2D event per piece)."""
+        from .tower import chunk_schedule
+        return chunk_schedule(R, min(self._infer_engine().chunk_images, max(R, 1)))
 
     def forward_chunked(self, x: Tensor, events) -> Tensor:
-        """forward() on a crop tensor that is still being filled by an H2D stream: chunk k may be
-        read once events[k] has completed (see training/clipself.py)."""
+        """forward() on a crop tensor that is still being filled by an H2D stream: piece k of
+        teacher_chunk_schedule() may be read once events[k] has completed (see training/clipself.py)."""
         return self._infer_engine().forward_cls(x, ready_events=events)
 
     def _prep(self, x: Tensor) -> Tensor:

@@ -66,6 +66,21 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def chunk_schedule(rows: int, step: int) -> List[tuple]:
+    """(start, count) pieces of a teacher pass over `rows` crops: a short first and second piece (step/4,
+    step/2) so the pass can start as soon as the first few crops have crossed PCIe, then full `step`s."""
+    out, s = [], 0
+    for n in (max(step // 4, 1), max(step // 2, 1)):
+        if rows - s > step:                  # only worth splitting when more than one full piece remains
+            out.append((s, n))
+            s += n
+    while s < rows:
+        n = min(step, rows - s)
+        out.append((s, n))
+        s += n
+    return out
+
+
 def input_grid(images: Tensor, cfg: "TowerCfg") -> int:
     """Token grid of an input batch. Like the reference's towers (eva_vit_model.py:533-549) any square
     resolution that is a multiple of the patch size is accepted; the grid is capped by the RoPE table the
@@ -304,10 +319,10 @@ class TowerEngine:
         step = min(self.chunk_images, R)
         ws = self.workspace(step)
         cls_ln = torch.empty(step, cfg.width, device=self.device, dtype=torch.bfloat16)
+        pieces = chunk_schedule(R, step) if ready_events is not None else [(s, min(step, R - s)) for s in range(0, R, step)]
         if ready_events is not None:
-            assert len(ready_events) == (R + step - 1) // step
-        for k, s in enumerate(range(0, R, step)):
-            n = min(step, R - s)
+            assert len(ready_events) == len(pieces)
+        for k, (s, n) in enumerate(pieces):
             if ready_events is not None:
                 torch.cuda.current_stream().wait_event(ready_events[k])
             self.embed(images[s:s + n], ws.x)

@@ -29,28 +29,38 @@ class CLIPSelf:
         self._copy_stream = None
         self._crops_dev = None
         self._crops_free = None
+        self._images_dev = None
+        self._images_free = None
 
-    def _stream_crops(self, image_crops, valid, R, device, dtype, chunk):
-        """Copy only the valid crops host->device on a side stream, one event per teacher chunk, so
-        the PCIe transfer overlaps the student forward and the earlier teacher chunks.
-        Runs of consecutive valid rows go as single cudaMemcpyAsync calls straight from the
-        (pinned) batch tensor: no host-side gather."""
+    def _stream_inputs(self, images, image_crops, valid, R, device, dtype, pieces):
+        """Host->device copies of one step on a side stream, in the order the step consumes them: the
+        student images first, then only the valid crops, one event per teacher piece, so the PCIe transfer
+        overlaps the student forward and the earlier teacher pieces.  Runs of consecutive valid rows go as
+        single cudaMemcpyAsync calls straight from the (pinned) batch tensor: no host-side gather."""
         B, K = valid.shape
         flat = image_crops.reshape(B * K, *image_crops.shape[2:])
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=device)
             self._crops_free = torch.cuda.Event()
+            self._images_free = torch.cuda.Event()
+        cs = self._copy_stream
+        if self._images_dev is None or self._images_dev.shape != images.shape or self._images_dev.dtype != dtype:
+            self._images_dev = torch.empty(images.shape, device=device, dtype=dtype)
+        else:
+            cs.wait_event(self._images_free)            # previous step's student forward has read them
         if self._crops_dev is None or self._crops_dev.shape[0] < R or self._crops_dev.shape[1:] != flat.shape[1:] \
                 or self._crops_dev.dtype != dtype:
             self._crops_dev = torch.empty((B * K,) + tuple(flat.shape[1:]), device=device, dtype=dtype)
         else:
-            self._copy_stream.wait_event(self._crops_free)      # previous step's teacher is done reading
+            cs.wait_event(self._crops_free)             # previous step's teacher is done reading
         dev = self._crops_dev
         idx = valid.flatten().nonzero().flatten().tolist()
         events = []
-        with torch.cuda.stream(self._copy_stream):
-            for s0 in range(0, R, chunk):
-                n = min(chunk, R - s0)
+        with torch.cuda.stream(cs):
+            self._images_dev.copy_(images, non_blocking=True)
+            images_ready = torch.cuda.Event()
+            images_ready.record(cs)
+            for s0, n in pieces:
                 a = s0
                 while a < s0 + n:                               # maximal run of consecutive source rows
                     b = a + 1
@@ -59,9 +69,9 @@ class CLIPSelf:
                     dev[a:b].copy_(flat[idx[a]:idx[a] + (b - a)], non_blocking=True)
                     a = b
                 ev = torch.cuda.Event()
-                ev.record(self._copy_stream)
+                ev.record(cs)
                 events.append(ev)
-        return dev[:R], events
+        return self._images_dev, images_ready, dev[:R], events
 
     def __call__(self, batch, model, dist_model, loss, device, cast_dtype, distributed, args):
         if distributed:
@@ -73,6 +83,7 @@ class CLIPSelf:
         B, K = normed_boxes.shape[:2]
 
         crop_events = None
+        streamed_images = False
         if normed_boxes.device.type == "cpu":
             # host-side, bit-exact: valid = boxes[..., 4] > 0.5, image-major order (clipself.py:29-36)
             boxes32 = normed_boxes.float()
@@ -83,8 +94,13 @@ class CLIPSelf:
             R = int(offsets[-1])
             rois = boxes32[valid][:, :4].contiguous().to(device, non_blocking=True)
             offsets = offsets.to(device, non_blocking=True)
-            crops, crop_events = self._stream_crops(image_crops, valid, R, device, dtype,
-                                                    dist_model.visual.teacher_chunk_images())
+            if images.device.type == "cpu":
+                images, images_ready, crops, crop_events = self._stream_inputs(
+                    images, image_crops, valid, R, device, dtype, dist_model.visual.teacher_chunk_schedule(R))
+                torch.cuda.current_stream().wait_event(images_ready)
+                streamed_images = True
+            else:
+                raise ValueError("boxes on the host but images on the device: pass the whole batch on one side")
         else:
             rois_all, crop_index, _, offsets = ops.extract_rois(normed_boxes.float().contiguous())
             R = int(offsets[-1])                         # the step's single device->host sync
@@ -92,7 +108,8 @@ class CLIPSelf:
             flat = image_crops.reshape(B * K, *image_crops.shape[2:])
             crops = ops.gather_rows(flat.contiguous(), crop_index, R) if R != B * K else flat
             crops = crops.to(dtype)
-        images = images.to(device=device, dtype=dtype, non_blocking=True)
+        if not streamed_images:
+            images = images.to(device=device, dtype=dtype, non_blocking=True)
 
         if getattr(args, "multiscale", False):
             cur_h, cur_w = images.shape[2:]
@@ -110,6 +127,8 @@ class CLIPSelf:
         # student forward first: it only needs the (small) images, so it overlaps the crop H2D stream
         model.visual.sync_gradients = bool(distributed)
         student_roi_features = model.visual.roi_features_packed(images, rois, offsets, R)
+        if streamed_images:
+            self._images_free.record()
         with torch.no_grad():
             if crop_events is not None:
                 teacher_crop_features = dist_model.visual.forward_chunked(crops, crop_events)

@@ -161,3 +161,13 @@ def test_open_clip_namespace_and_cliploss():
         sys.path.remove(os.path.join(root, "compat"))
         for m in [k for k in sys.modules if k == "open_clip" or k.startswith("training")]:
             sys.modules.pop(m, None)
+
+
+def test_teacher_chunk_schedule_covers_every_crop_once():
+    from clipself_b200.tower import chunk_schedule
+    for rows, step in [(2048, 256), (256, 256), (300, 256), (600, 256), (5, 4), (9, 4), (1, 1), (0, 1), (513, 256)]:
+        pieces = chunk_schedule(rows, step)
+        assert sum(n for _, n in pieces) == rows
+        assert all(0 < n <= step for _, n in pieces)
+        assert [s for s, _ in pieces] == [sum(n for _, n in pieces[:i]) for i in range(len(pieces))]
+    assert chunk_schedule(2048, 256)[:3] == [(0, 64), (64, 128), (192, 256)]      # short pieces first
