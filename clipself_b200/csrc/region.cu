@@ -197,19 +197,23 @@ roi_align_fwd_kernel(const float* __restrict__ fmap, int H, int W, int C, const 
 // d_fmap[b,y,x,c] = sum_{r in image b} wy[r,y] wx[r,x] d_out[r,c];  grid (C/64, B).
 // The image's gradient slice [H*W][64] is accumulated in shared memory, box after box in index order
 // (deterministic, no atomics: inside one box every (pixel, channel) belongs to one thread), and written
-// to HBM once.
+// to HBM once.  Per chunk of 64 boxes the weights, the d_out rows and the support windows are staged /
+// precomputed in shared memory, so the serial per-box loop touches no global memory.
 template <bool kStage>
 __global__ void __launch_bounds__(ROI_THREADS)
 roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const int* __restrict__ img_offsets,
                      const float* __restrict__ wy, const float* __restrict__ wx, float* __restrict__ d_fmap) {
     extern __shared__ float s_dyn[];
-    float* s_wy = s_dyn;
-    float* s_wx = s_wy + ROI_CHUNK * H;
-    float* s_acc = s_wx + ROI_CHUNK * W;             // [H*W][ROI_CS] when staged
+    float* s_wy = s_dyn;                             // [ROI_CHUNK][H]
+    float* s_wx = s_wy + ROI_CHUNK * H;              // [ROI_CHUNK][W]
+    float* s_go = s_wx + ROI_CHUNK * W;              // [ROI_CHUNK][ROI_CS]
+    int4* s_win = reinterpret_cast<int4*>(s_go + ROI_CHUNK * ROI_CS);   // [ROI_CHUNK] (ylo, yhi, xlo, xhi)
+    float* s_acc = reinterpret_cast<float*>(s_win + ROI_CHUNK);         // [H*W][ROI_CS] when staged
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * ROI_CS;
     const int c = threadIdx.x % ROI_CS;
     const int lane = threadIdx.x / ROI_CS;
+    const int warp = threadIdx.x / 32;
     const int begin = img_offsets[b], end = img_offsets[b + 1];
     const bool c_ok = c0 + c < C;
     float* g = d_fmap + (long long)b * H * W * C + c0;
@@ -225,23 +229,33 @@ roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const
         __syncthreads();
         for (int i = threadIdx.x; i < n * H; i += ROI_THREADS) s_wy[i] = wy[(long long)r0 * H + i];
         for (int i = threadIdx.x; i < n * W; i += ROI_THREADS) s_wx[i] = wx[(long long)r0 * W + i];
+        for (int i = threadIdx.x; i < n * ROI_CS; i += ROI_THREADS) {
+            const int rr = i / ROI_CS, cc = i % ROI_CS;
+            s_go[i] = (c0 + cc < C) ? d_out[(long long)(r0 + rr) * C + c0 + cc] : 0.f;
+        }
         __syncthreads();
-        for (int rr = 0; rr < n; ++rr) {            // boxes in order; the 4 lanes split the window's pixels
+        for (int rr = warp; rr < n; rr += ROI_THREADS / 32) {       // one warp per box: support windows
+            int ylo, yhi, xlo, xhi;
+            support(s_wy + rr * H, H, ylo, yhi);
+            support(s_wx + rr * W, W, xlo, xhi);
+            if ((threadIdx.x & 31) == 0) s_win[rr] = make_int4(ylo, yhi, xlo, xhi);
+        }
+        __syncthreads();
+        for (int rr = 0; rr < n; ++rr) {            // boxes in order; the lanes split the window's pixels
+            const int4 win = s_win[rr];
+            const int ww = max(win.w - win.z + 1, 0);               // degenerate boxes have an empty support
+            const int npx = max(win.y - win.x + 1, 0) * ww;
+            if (npx == 0) continue;
             const float* wyr = s_wy + rr * H;
             const float* wxr = s_wx + rr * W;
-            int ylo, yhi, xlo, xhi;
-            support(wyr, H, ylo, yhi);
-            support(wxr, W, xlo, xhi);
-            const float go = c_ok ? d_out[(long long)(r0 + rr) * C + c0 + c] : 0.f;
-            const int ww = max(xhi - xlo + 1, 0);                  // degenerate boxes have an empty support
-            const int npx = max(yhi - ylo + 1, 0) * ww;
+            const float go = s_go[rr * ROI_CS + c];
             for (int q = lane; q < npx; q += ROI_LANES) {
-                const int y = ylo + q / ww, x = xlo + q % ww;
+                const int y = win.x + q / ww, x = win.z + q % ww;
                 const float v = wyr[y] * wxr[x] * go;
                 if (kStage) s_acc[(y * W + x) * ROI_CS + c] += v;
                 else if (c_ok) g[(long long)(y * W + x) * C + c] += v;
             }
-            if (npx > 0) __syncthreads();            // the next box may overlap this one's pixels (other lanes)
+            __syncthreads();                        // the next box may overlap this one's pixels (other lanes)
         }
     }
     if (kStage) {
@@ -257,57 +271,69 @@ roi_align_bwd_kernel(const float* __restrict__ d_out, int H, int W, int C, const
     }
 }
 
-// out[r,c] = sum_p m[r,p] f[b,p,c] / (sum_p m[r,p] + 1e-12);  grid (C/64, B).
-// Pixel chunks of the map slice and of the image's masks are staged in shared memory; every thread keeps
-// the accumulators of its boxes (one channel, every 4th box) in registers.
-constexpr int MP_PX = 64;        // pixels per staged chunk
-constexpr int MP_ACC = 8;        // boxes per thread per pass (x 8 lanes = 64 boxes per pass)
-__global__ void __launch_bounds__(ROI_THREADS)
+// out[r,c] = sum_p m[r,p] f[b,p,c] / (sum_p m[r,p] + 1e-12);  grid (C/128, B).
+// A small [boxes x pixels] x [pixels x channels] product on the CUDA cores: pixel chunks of the map slice
+// and of the image's masks are staged in shared memory; every thread keeps an 8-box x 4-channel register
+// tile (one LDS.128 of the map and 8 broadcast mask reads feed 32 FMAs).
+constexpr int MP_CS = 128;       // channels per CTA (32 threads x float4)
+constexpr int MP_PX = 32;        // pixels per staged chunk
+constexpr int MP_ACC = 8;        // boxes per thread per pass
+constexpr int MP_LANES = 8;      // box lanes (warps) per CTA -> 64 boxes per pass
+constexpr int MP_THREADS = 32 * MP_LANES;
+__global__ void __launch_bounds__(MP_THREADS)
 mask_pool_kernel(const float* __restrict__ fmap, int HW, int C, const float* __restrict__ masks,
                  const int* __restrict__ img_offsets, float* __restrict__ out) {
-    __shared__ float s_f[MP_PX][ROI_CS];
-    __shared__ float s_m[MP_ACC * ROI_LANES][MP_PX + 1];
+    __shared__ __align__(16) float s_f[MP_PX][MP_CS];
+    __shared__ float s_m[MP_ACC * MP_LANES][MP_PX + 1];
     const int b = blockIdx.y;
-    const int c0 = blockIdx.x * ROI_CS;
-    const int c = threadIdx.x % ROI_CS;
-    const int lane = threadIdx.x / ROI_CS;
+    const int c0 = blockIdx.x * MP_CS;
+    const int ct = threadIdx.x % 32;                 // channel quad
+    const int lane = threadIdx.x / 32;               // = warp: all 32 threads read the same mask value
     const int begin = img_offsets[b], end = img_offsets[b + 1];
     const float* g = fmap + (long long)b * HW * C + c0;
-    const bool c_ok = c0 + c < C;
-    for (int r0 = begin; r0 < end; r0 += MP_ACC * ROI_LANES) {
-        const int n = min(MP_ACC * ROI_LANES, end - r0);
-        float acc[MP_ACC], msum[MP_ACC];
+    for (int r0 = begin; r0 < end; r0 += MP_ACC * MP_LANES) {
+        const int n = min(MP_ACC * MP_LANES, end - r0);
+        float acc[MP_ACC][4], msum[MP_ACC];
 #pragma unroll
-        for (int k = 0; k < MP_ACC; ++k) acc[k] = msum[k] = 0.f;
+        for (int k = 0; k < MP_ACC; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = msum[k] = 0.f;
         for (int p0 = 0; p0 < HW; p0 += MP_PX) {
             const int np = min(MP_PX, HW - p0);
             __syncthreads();
-            for (int i = threadIdx.x; i < np * ROI_CS; i += ROI_THREADS) {
-                const int p = i / ROI_CS, cc = i % ROI_CS;
-                s_f[p][cc] = (c0 + cc < C) ? g[(long long)(p0 + p) * C + cc] : 0.f;
+            for (int i = threadIdx.x; i < np * (MP_CS / 4); i += MP_THREADS) {
+                const int p = i / (MP_CS / 4), c4 = (i % (MP_CS / 4)) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + c4 + 3 < C) v = *reinterpret_cast<const float4*>(g + (long long)(p0 + p) * C + c4);
+                else
+                    for (int z = 0; z < 4; ++z)
+                        if (c0 + c4 + z < C) (&v.x)[z] = g[(long long)(p0 + p) * C + c4 + z];
+                *reinterpret_cast<float4*>(&s_f[p][c4]) = v;
             }
-            for (int i = threadIdx.x; i < n * np; i += ROI_THREADS) {
+            for (int i = threadIdx.x; i < MP_ACC * MP_LANES * np; i += MP_THREADS) {
                 const int rr = i / np, p = i % np;
-                s_m[rr][p] = masks[(long long)(r0 + rr) * HW + p0 + p];
+                s_m[rr][p] = rr < n ? masks[(long long)(r0 + rr) * HW + p0 + p] : 0.f;
             }
             __syncthreads();
             for (int p = 0; p < np; ++p) {
-                const float f = s_f[p][c];
+                const float4 f = *reinterpret_cast<const float4*>(&s_f[p][ct * 4]);
 #pragma unroll
                 for (int k = 0; k < MP_ACC; ++k) {
-                    const int rr = k * ROI_LANES + lane;
-                    if (rr < n) {
-                        const float w = s_m[rr][p];
-                        acc[k] = fmaf(w, f, acc[k]);
-                        msum[k] += w;
-                    }
+                    const float w = s_m[k * MP_LANES + lane][p];
+                    acc[k][0] = fmaf(w, f.x, acc[k][0]);
+                    acc[k][1] = fmaf(w, f.y, acc[k][1]);
+                    acc[k][2] = fmaf(w, f.z, acc[k][2]);
+                    acc[k][3] = fmaf(w, f.w, acc[k][3]);
+                    msum[k] += w;
                 }
             }
         }
 #pragma unroll
         for (int k = 0; k < MP_ACC; ++k) {
-            const int rr = k * ROI_LANES + lane;
-            if (rr < n && c_ok) out[(long long)(r0 + rr) * C + c0 + c] = acc[k] / (msum[k] + 1e-12f);
+            const int rr = k * MP_LANES + lane;
+            if (rr >= n) continue;
+            const float inv = 1.f / (msum[k] + 1e-12f);
+            float* o = out + (long long)(r0 + rr) * C + c0 + ct * 4;
+            for (int z = 0; z < 4; ++z)
+                if (c0 + ct * 4 + z < C) o[z] = acc[k][z] * inv;
         }
     }
 }
@@ -455,8 +481,8 @@ extern "C" int cs_gather_rows(const void* src, const int32_t* index, int R, int6
     return CS_OK;
 }
 
-static int roi_smem_bytes(int H, int W, bool stage) {
-    return (ROI_CHUNK * (H + W) + (stage ? H * W * ROI_CS : 0)) * (int)sizeof(float);
+static int roi_smem_bytes(int H, int W, bool stage, bool bwd = false) {
+    return (ROI_CHUNK * (H + W) + (stage ? H * W * ROI_CS : 0) + (bwd ? ROI_CHUNK * (ROI_CS + 4) : 0)) * (int)sizeof(float);
 }
 constexpr int kMaxStage = 200 * 1024;
 
@@ -492,8 +518,8 @@ extern "C" int cs_roi_align_bwd(const float* d_out, int B, int H, int W, int C, 
     CS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R >= 0 && H + W <= 384, "cs_roi_align_bwd: bad shape");
     CS_CHECK_ARG((uintptr_t)d_fmap % 16 == 0 && C % 4 == 0, "cs_roi_align_bwd: d_fmap must be 16 B aligned, C %% 4 == 0");
     dim3 grid(ceil_div(C, ROI_CS), B);
-    const bool stage = roi_smem_bytes(H, W, true) <= kMaxStage;
-    const int smem = roi_smem_bytes(H, W, stage);
+    const bool stage = roi_smem_bytes(H, W, true, true) <= kMaxStage;
+    const int smem = roi_smem_bytes(H, W, stage, true);
     static bool configured = false;
     if (!configured) {
         CS_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStage));
@@ -512,8 +538,9 @@ extern "C" int cs_mask_pool_fwd(const float* fmap, int B, int HW, int C, const f
     CS_CHECK_ARG(fmap && masks && img_offsets && out, "cs_mask_pool_fwd: null pointer");
     CS_CHECK_ARG(B > 0 && HW > 0 && C > 0 && R >= 0, "cs_mask_pool_fwd: bad shape");
     if (R == 0) return CS_OK;
-    dim3 grid(ceil_div(C, ROI_CS), B);
-    mask_pool_kernel<<<grid, ROI_THREADS, 0, (cudaStream_t)stream>>>(fmap, HW, C, masks, img_offsets, out);
+    CS_CHECK_ARG((uintptr_t)fmap % 16 == 0 && C % 4 == 0, "cs_mask_pool_fwd: fmap must be 16 B aligned, C %% 4 == 0");
+    dim3 grid(ceil_div(C, MP_CS), B);
+    mask_pool_kernel<<<grid, MP_THREADS, 0, (cudaStream_t)stream>>>(fmap, HW, C, masks, img_offsets, out);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
