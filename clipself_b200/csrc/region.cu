@@ -40,6 +40,11 @@ __global__ void extract_rois_kernel(const float* __restrict__ boxes, int B, int 
         crop_index[dst] = i;
         roi_batch[dst] = b;
     }
+    for (int i = s_off[B] + threadIdx.x; i < B * K; i += blockDim.x) {     // rows past the valid count: zeros
+        rois[i * 4 + 0] = rois[i * 4 + 1] = rois[i * 4 + 2] = rois[i * 4 + 3] = 0.f;
+        crop_index[i] = 0;
+        roi_batch[i] = 0;
+    }
 }
 
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ index,

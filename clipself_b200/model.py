@@ -112,7 +112,8 @@ class _RoiFeatures(torch.autograd.Function):
         if visual.sync_gradients and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             # the ONE collective of the step: mean all-reduce of the flat student gradient (NCCL/NVLink)
-            torch.distributed.all_reduce(eng.flat_grad[:eng.layout.n_grad], op=torch.distributed.ReduceOp.AVG)
+            torch.distributed.all_reduce(eng.flat_grad[eng.layout.decay_start(eng.first_trainable):eng.layout.n_grad],
+                                         op=torch.distributed.ReduceOp.AVG)
         grads = []
         for name, p in visual._block_params():
             if name in eng.layout.gradless or not p.requires_grad:
@@ -256,10 +257,12 @@ class EVAVisionTransformer(nn.Module):
         """Flat-buffer engine for the trainable tower; block parameters are re-pointed at views of
         the flat f32 buffer so any optimizer updates it in place."""
         self._check_cuda()
-        trainable = [p.requires_grad for _, p in self._block_params()]
-        if not all(trainable):
-            raise NotImplementedError("the fused training path needs every block unlocked "
-                                      "(--lock-image-unlocked-groups == depth, as in the reference scripts)")
+        flags = [all(p.requires_grad for p in blk.parameters()) for blk in self.blocks]
+        mixed = [any(p.requires_grad for p in blk.parameters()) for blk in self.blocks]
+        first = flags.index(True) if True in flags else len(flags)
+        if first == len(flags) or flags != mixed or not all(flags[first:]):
+            raise NotImplementedError("the fused training path needs a trainable suffix of whole blocks "
+                                      "(lock_image_tower(unlocked_groups=n) unfreezes blocks[-n:], as the reference does)")
         if self._student is None:
             self._student = StudentEngine(self.cfg, self._tower_sd(), self._device())
         eng = self._student
@@ -268,6 +271,7 @@ class EVAVisionTransformer(nn.Module):
             if p.data_ptr() != v.data_ptr():
                 v.copy_(p.data)
                 p.data = v
+        eng.first_trainable = first
         eng.repack()
         return eng
 

@@ -49,9 +49,9 @@ def extract_rois(normed_boxes: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     B, K, five = normed_boxes.shape
     assert five == 5
     dev = normed_boxes.device
-    rois = torch.zeros(B * K, 4, device=dev, dtype=torch.float32)
-    crop_index = torch.zeros(B * K, device=dev, dtype=torch.int32)
-    roi_batch = torch.zeros(B * K, device=dev, dtype=torch.int32)
+    rois = torch.empty(B * K, 4, device=dev, dtype=torch.float32)       # rows past the valid count are zeroed by the kernel
+    crop_index = torch.empty(B * K, device=dev, dtype=torch.int32)
+    roi_batch = torch.empty(B * K, device=dev, dtype=torch.int32)
     offsets = torch.empty(B + 1, device=dev, dtype=torch.int32)
     call("cs_extract_rois", _p(normed_boxes), B, K, _p(rois), _p(crop_index), _p(roi_batch), _p(offsets), _stream())
     return rois, crop_index, roi_batch, offsets

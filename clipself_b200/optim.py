@@ -35,10 +35,11 @@ class FusedAdamW:
         self.step_count += 1
         b1, b2 = self.betas
         nd, ng = lay.n_decay, lay.n_grad
+        ds, ns = lay.decay_start(e.first_trainable), lay.nodecay_start(e.first_trainable)   # frozen blocks are skipped
         g_decay, g_nodecay = self.param_groups[1], self.param_groups[0]
-        ops.adamw_step(e.flat_param[:nd], e.flat_grad[:nd], self.exp_avg[:nd], self.exp_avg_sq[:nd],
+        ops.adamw_step(e.flat_param[ds:nd], e.flat_grad[ds:nd], self.exp_avg[ds:nd], self.exp_avg_sq[ds:nd],
                        g_decay["lr"], b1, b2, self.eps, g_decay["weight_decay"], self.step_count, grad_scale)
-        ops.adamw_step(e.flat_param[nd:ng], e.flat_grad[nd:ng], self.exp_avg[nd:ng], self.exp_avg_sq[nd:ng],
+        ops.adamw_step(e.flat_param[ns:ng], e.flat_grad[ns:ng], self.exp_avg[ns:ng], self.exp_avg_sq[ns:ng],
                        g_nodecay["lr"], b1, b2, self.eps, g_nodecay["weight_decay"], self.step_count, grad_scale)
 
     def state_dict(self):

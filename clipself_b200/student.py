@@ -95,6 +95,17 @@ class FlatLayout:
         self.n_total = off                      # [n_grad, n_total): parameters that never get a gradient
         self.gradless = tuple(tail)
 
+    def decay_start(self, first_block: int) -> int:
+        """Start of the weight-decay range of blocks[first_block:] (blocks are laid out in order)."""
+        if first_block <= 0:
+            return 0
+        return min(o for o in (self.offset[f"blocks.{first_block}.{nm}"] for nm in W_NAMES) if o < self.n_decay)
+
+    def nodecay_start(self, first_block: int) -> int:
+        if first_block <= 0:
+            return self.n_decay
+        return min(o for o in (self.offset[f"blocks.{first_block}.{nm}"] for nm in V_NAMES) if o < self.n_grad)
+
     def view(self, flat: Tensor, name: str) -> Tensor:
         o = self.offset[name]
         shape = self.shape[name]
@@ -186,6 +197,9 @@ class StudentEngine:
         self._alloc_packs()
         self.scale = cfg.head_dim ** -0.5
         self._tape: Optional[_Tape] = None
+        # blocks[:first_trainable] are frozen (lock_image_tower(unlocked_groups=n) unfreezes blocks[-n:],
+        # eva_vit_model.py:500-516): no gradient, no all-reduce, no optimizer update for them
+        self.first_trainable = 0
         self.repack()
 
     # ------------------------------------------------------------------ packing
@@ -353,12 +367,13 @@ class StudentEngine:
         ops.cast_transpose(t.d_head, Mp, cfg.embed_dim, dst=t.d_head_bf)
         d_tok = t.g_D2[:Mp]
         ops.gemm(t.d_head_bf, self.head_wT, d_tok, M=Mp)
-        self.flat_grad[:self.layout.n_decay].zero_()                 # split-K wgrad GEMMs accumulate with red.add
+        k0 = self.first_trainable
+        self.flat_grad[self.layout.decay_start(k0):self.layout.n_decay].zero_()   # split-K wgrad GEMMs accumulate with red.add
         dx = t.dx
         dx.zero_()                                                     # CLS rows get no gradient from the tail
         ops.layernorm_bwd_dx(d_tok, t.x[cfg.layers], Mp, D, t.tok_stats[0], t.tok_stats[1], fr.norm_g, dx,
                              row_div=g2, row_off=1, row_mapped=True)
-        for i in range(cfg.layers - 1, -1, -1):
+        for i in range(cfg.layers - 1, k0 - 1, -1):
             pk, st = self.packs[i], t.stats[i]
             last = i == cfg.layers - 1
             # ---- MLP branch: x_out = xmid + w3(hln) + b3
@@ -419,5 +434,5 @@ class StudentEngine:
                 ops.gemm(d_att, pk.wvT, t.g_D2, M=M)
             ops.col_reduce(t.g_D2, M, D, self.g(i, "norm1.bias"), ws, x=t.x[i], mean=st[0], rstd=st[1],
                            dgamma=self.g(i, "norm1.weight"))
-            if i > 0:   # the embedding below block 0 is frozen: its input gradient is not needed
+            if i > k0:  # everything below the first trainable block is frozen: its input gradient is not needed
                 ops.layernorm_bwd_dx(t.g_D2, t.x[i], M, D, st[0], st[1], self.p(i, "norm1.weight"), dx, add=dx)

@@ -46,7 +46,7 @@ int cs_device_info(int* sm_out, int* num_sms_out, int64_t* hbm_bytes_out);
 /* Valid-box / crop index extraction — replaces clipself.py:29-36.
  *   normed_boxes [B,K,5] f32 (x0,y0,x1,y1,valid).  valid := box[4] > 0.5.
  * Outputs, image-major and order-preserving (bit-exact copies of the inputs):
- *   rois      [B*K,4] f32  first R rows filled          (== cat(rois_list))
+ *   rois      [B*K,4] f32  first R rows filled, the rest zeroed   (== cat(rois_list))
  *   crop_index[B*K]   i32  flat index b*K+k of each kept row (== index into image_crops.flatten(0,1))
  *   roi_batch [B*K]   i32  image index of each kept row
  *   img_offsets[B+1]  i32  exclusive prefix sum of per-image counts; img_offsets[B] == R      */

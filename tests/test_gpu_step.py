@@ -235,3 +235,43 @@ def test_multiscale_step_vs_oracle(want):
         r = rel(params[k].grad.cpu().numpy(), ssd[k].grad.numpy())
         print(f"  {k}: rel-L2 {r:.3e}")
         assert r <= 0.08, (k, r)
+
+
+def test_partially_unlocked_tower(golden):
+    """--lock-image-unlocked-groups 2 on the 3-block tower: block 0 frozen (no gradient, untouched by the
+    optimizer), blocks 1-2 get the same gradients as in the fully unlocked golden run."""
+    from clipself_b200.optim import FusedAdamW
+    from clipself_b200.training.clipself import CLIPSelf
+    g = golden("tiny_ragged")
+    ocfg, B, K, kind, ragged = CASES["tiny_ragged"]
+    seed = int(g["seed"])
+    dev = torch.device("cuda")
+    student, teacher = build_model(ocfg, seed, dev), build_model(ocfg, seed + 1, dev)
+    student.lock_image_tower(unlocked_groups=2)
+    student.train()
+    teacher.eval()
+    batch = O.synth_batch(ocfg, B, K, seed + 2, kind=kind, ragged=ragged)
+    args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+    losses, _, _ = CLIPSelf()(batch, student, teacher, None, dev, None, False, args)
+    assert abs(losses["loss_cosine"].item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    losses["loss_cosine"].backward()
+    params = dict(student.visual.named_parameters())
+    checked = 0
+    for name, ref_norm in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        if not name.startswith("blocks."):
+            continue
+        p = params[name]
+        if name.startswith("blocks.0.") or ref_norm < 0:
+            assert p.grad is None, name
+            continue
+        assert rel(p.grad.cpu().numpy(), g["grad/" + name]) <= 0.08, name
+        checked += 1
+    assert checked > 20
+    before = {k: v.detach().clone() for k, v in params.items() if k.startswith("blocks.")}
+    FusedAdamW(student.visual._student, lr=1e-2, weight_decay=0.1).step()
+    torch.cuda.synchronize()
+    for k, v in before.items():
+        changed = not torch.equal(params[k].detach(), v)
+        frozen = k.startswith("blocks.0.") or k in ("blocks.2.attn.q_proj.weight", "blocks.2.attn.k_proj.weight",
+                                                   "blocks.2.attn.q_bias")
+        assert changed != frozen, k

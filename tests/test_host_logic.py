@@ -171,3 +171,20 @@ def test_teacher_chunk_schedule_covers_every_crop_once():
         assert all(0 < n <= step for _, n in pieces)
         assert [s for s, _ in pieces] == [sum(n for _, n in pieces[:i]) for i in range(len(pieces))]
     assert chunk_schedule(2048, 256)[:3] == [(0, 64), (64, 128), (192, 256)]      # short pieces first
+
+
+def test_flat_layout_trainable_suffix_ranges():
+    """lock_image_tower(unlocked_groups=n) trains blocks[-n:]: their parameters must be exactly the two
+    suffix ranges the optimizer / all-reduce use."""
+    from clipself_b200.student import FlatLayout
+    from clipself_b200.tower import TowerCfg
+    lay = FlatLayout(TowerCfg(image_size=64, patch=16, width=128, heads=2, layers=3, hidden=384, embed_dim=64))
+    assert (lay.decay_start(0), lay.nodecay_start(0)) == (0, lay.n_decay)
+    for k in range(3):
+        ds, ns = lay.decay_start(k), lay.nodecay_start(k)
+        for name, o in lay.offset.items():
+            if name in lay.gradless:
+                assert o >= lay.n_grad
+                continue
+            inside = ds <= o < lay.n_decay or ns <= o < lay.n_grad
+            assert inside == (int(name.split(".")[1]) >= k), (k, name)
