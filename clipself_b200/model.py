@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .student import StudentEngine
+from .student import StudentEngine, allreduce_flat_gradient
 from .tower import TowerCfg, TowerEngine, input_grid, rope_tables
 
 Tensor = torch.Tensor
@@ -109,11 +109,9 @@ class _RoiFeatures(torch.autograd.Function):
         img_offsets, wy, wx = ctx.saved_tensors
         d_dense = ops.roi_align_bwd(d_out.contiguous(), ctx.shape, img_offsets, ctx.R, wy, wx)
         eng.backward(d_dense)
-        if visual.sync_gradients and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
+        if visual.sync_gradients:
             # the ONE collective of the step: mean all-reduce of the flat student gradient (NCCL/NVLink)
-            torch.distributed.all_reduce(eng.flat_grad[eng.layout.decay_start(eng.first_trainable):eng.layout.n_grad],
-                                         op=torch.distributed.ReduceOp.AVG)
+            allreduce_flat_gradient(eng.flat_grad, eng.layout, eng.first_trainable)
         grads = []
         for name, p in visual._block_params():
             if name in eng.layout.gradless or not p.requires_grad:

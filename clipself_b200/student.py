@@ -3,11 +3,14 @@
 Reference semantics being reproduced (wusize/CLIPSelf @ 1c7fe9c):
   forward   EVAVisionTransformer.encode_dense            eva_vit_model.py:588-623
   backward  torch autograd through the above, for the parameters left trainable by
-            EVAVisionTransformer.lock(unlocked_groups=depth)        eva_vit_model.py:500-516
-            (all of visual.blocks.*; the last block's q_proj/k_proj/q_bias never receive a
-            gradient because forward_without_attn skips them, eva_vit_model.py:249-256, 317-324)
-  grad sync one mean all-reduce over the flat gradient buffer (what DDP at main.py:188 is meant to do;
-            SURVEY.md fact 7) — issued by the caller (training/clipself.py) on `flat_grad[:n_grad]`.
+            EVAVisionTransformer.lock(unlocked_groups=n)            eva_vit_model.py:500-516
+            (visual.blocks[-n:], n = depth in the scripts; the last block's q_proj/k_proj/q_bias never
+            receive a gradient because forward_without_attn skips them, eva_vit_model.py:249-256, 317-324)
+  grad sync one mean all-reduce over the trainable range of the flat gradient buffer (what DDP at
+            main.py:188 is meant to do) — issued at the end of the backward
+            (model.py: _RoiFeatures.backward) on `flat_grad[decay_start(first_trainable):n_grad]`.
+  input     any square resolution up to a 64 x 64 token grid (--det-image-size / --multiscale):
+            RoPE tables and pos_embed per resolution, rope.py:179-214, eva_vit_model.py:631-643.
 
 Memory layout (HBM, all f32, one allocation each for params / grads / Adam moments):
   [ 2-D weights of every block, in GEMM-friendly groups | 1-D vectors | grad-less tail ]
@@ -116,6 +119,22 @@ class FlatLayout:
 
     def names(self) -> List[str]:
         return list(self.offset.keys())
+
+
+def allreduce_flat_gradient(flat_grad: Tensor, layout: FlatLayout, first_trainable: int = 0) -> None:
+    """The ONE collective of the step: mean all-reduce of the trainable range of the flat
+    gradient buffer — NCCL over NVLink / NVSwitch on the GPUs (`ReduceOp.AVG`); backends without AVG (gloo,
+    used by the CPU tests) sum and scale.  The grad-less tail and the weights of frozen blocks are never sent
+    (the few 1-D vectors of frozen blocks lie inside the single contiguous span; they are zeros and unused)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    span = flat_grad[layout.decay_start(first_trainable):layout.n_grad]
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(span, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(span, op=dist.ReduceOp.SUM)
+        span /= dist.get_world_size()
 
 
 class _BlockPack:

@@ -46,11 +46,15 @@ class CLIPSelf:
         cs = self._copy_stream
         if self._images_dev is None or self._images_dev.shape != images.shape or self._images_dev.dtype != dtype:
             self._images_dev = torch.empty(images.shape, device=device, dtype=dtype)
+            # a fresh block from the caching allocator may still be read by kernels queued on the compute
+            # stream (the allocator only orders reuse within that stream): order the copies after them
+            cs.wait_stream(torch.cuda.current_stream())
         else:
             cs.wait_event(self._images_free)            # previous step's student forward has read them
         if self._crops_dev is None or self._crops_dev.shape[0] < R or self._crops_dev.shape[1:] != flat.shape[1:] \
                 or self._crops_dev.dtype != dtype:
             self._crops_dev = torch.empty((B * K,) + tuple(flat.shape[1:]), device=device, dtype=dtype)
+            cs.wait_stream(torch.cuda.current_stream())
         else:
             cs.wait_event(self._crops_free)             # previous step's teacher is done reading
         dev = self._crops_dev

@@ -22,14 +22,20 @@ def _worker(rank, world, port, out):
     g = torch.Generator().manual_seed(100 + rank)
     flat_grad = torch.randn(lay.n_total, generator=g)
     local = flat_grad.clone()
-    # the ONE collective of the step, on the with-gradient prefix only (gloo has no AVG: sum then scale)
-    dist.all_reduce(flat_grad[:lay.n_grad], op=dist.ReduceOp.SUM)
-    flat_grad[:lay.n_grad] /= world
+    # the ONE collective of the step (the function the autograd node calls), on the with-gradient prefix only
+    from clipself_b200.student import allreduce_flat_gradient
+    allreduce_flat_gradient(flat_grad, lay)
     gathered = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     mean = torch.stack(gathered).mean(0)
     ok = torch.allclose(flat_grad[:lay.n_grad], mean[:lay.n_grad], atol=1e-6) and \
         torch.equal(flat_grad[lay.n_grad:], local[lay.n_grad:])            # grad-less tail untouched
+    # partially unlocked tower (blocks[-2:] trainable): block 0's ranges must not be sent either
+    part = local.clone()
+    allreduce_flat_gradient(part, lay, first_trainable=1)
+    ds, ns = lay.decay_start(1), lay.nodecay_start(1)
+    ok = ok and torch.equal(part[:ds], local[:ds]) and torch.allclose(part[ds:lay.n_decay], mean[ds:lay.n_decay], atol=1e-6) \
+        and torch.allclose(part[ns:lay.n_grad], mean[ns:lay.n_grad], atol=1e-6) and torch.equal(part[lay.n_grad:], local[lay.n_grad:])
     # rank-sharded synthetic batches: different seeds per rank, same shapes (weak scaling)
     from clipself_b200.data import synthetic_batch
     b = synthetic_batch(64, 2, 4, "grid", seed=1234 + rank)
