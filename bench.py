@@ -141,8 +141,11 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if distributed:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"              # keep stdout to the single JSON line
+        # keep stdout to the single JSON line: NCCL prints its version banner (and any debug output) to stdout
+        # at every level >= VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     _lib.require_device()
     wl = WORKLOADS[args.workload]
