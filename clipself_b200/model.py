@@ -88,6 +88,23 @@ def _trunc_normal_(t: Tensor, std: float) -> None:
 # ----------------------------------------------------------------------------------------------
 # autograd glue: one node for the whole student dense+RoI path
 # ----------------------------------------------------------------------------------------------
+def _flat_grad_outputs(visual, eng: StudentEngine) -> list:
+    """Publish the gradients of one backward: `.grad` of every trainable blocks.* parameter is pointed at its
+    view of the flat gradient buffer the backward has just overwritten, and autograd gets None for them.
+    Handing the views to AccumulateGrad instead would add a view to itself (doubling the gradient) whenever
+    `.grad` survives from the previous step (optimizer.zero_grad(set_to_none=False), or no zero_grad at all).
+    `.grad` therefore always holds the gradient of the latest backward (accum_freq == 1, train.py:89)."""
+    grads = []
+    for name, p in visual._block_params():
+        grads.append(None)
+        if name in eng.layout.gradless or not p.requires_grad:
+            continue
+        v = eng.layout.view(eng.flat_grad, name)
+        if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+            p.grad = v
+    return grads
+
+
 class _RoiFeatures(torch.autograd.Function):
     """encode_dense -> RoIAlign.  forward/backward run entirely in the CUDA library; the node
     exposes the flat-buffer gradient views to autograd so optimizers see ordinary `.grad`s."""
@@ -112,12 +129,7 @@ class _RoiFeatures(torch.autograd.Function):
         if visual.sync_gradients:
             # the ONE collective of the step: mean all-reduce of the flat student gradient (NCCL/NVLink)
             allreduce_flat_gradient(eng.flat_grad, eng.layout, eng.first_trainable)
-        grads = []
-        for name, p in visual._block_params():
-            if name in eng.layout.gradless or not p.requires_grad:
-                grads.append(None)
-            else:
-                grads.append(eng.layout.view(eng.flat_grad, name))
+        grads = _flat_grad_outputs(visual, eng)
         return (None, None, None, None, None, *grads)
 
 
@@ -135,8 +147,7 @@ class _DenseFeatures(torch.autograd.Function):
         visual = ctx.visual
         eng: StudentEngine = visual._student
         eng.backward(d_dense.contiguous())
-        grads = [None if (n in eng.layout.gradless or not p.requires_grad) else eng.layout.view(eng.flat_grad, n)
-                 for n, p in visual._block_params()]
+        grads = _flat_grad_outputs(visual, eng)
         return (None, None, *grads)
 
 

@@ -275,3 +275,28 @@ def test_partially_unlocked_tower(golden):
         frozen = k.startswith("blocks.0.") or k in ("blocks.2.attn.q_proj.weight", "blocks.2.attn.k_proj.weight",
                                                    "blocks.2.attn.q_bias")
         assert changed != frozen, k
+
+
+def test_repeated_backward_does_not_double_gradients():
+    """`.grad` of the block parameters are views of the flat gradient buffer the backward overwrites: a second
+    step without zero_grad (or with set_to_none=False) must leave the new gradient, not twice it."""
+    from clipself_b200.training.clipself import CLIPSelf
+    ocfg = O.CFG_TINY
+    dev = torch.device("cuda")
+    student, teacher = build_model(ocfg, 91, dev), build_model(ocfg, 92, dev)
+    student.lock_image_tower(unlocked_groups=ocfg.layers)
+    batch = O.synth_batch(ocfg, 2, 4, 93, kind="grid")
+    args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+    method = CLIPSelf()
+    norms = []
+    for it in range(3):
+        if it == 2:
+            student.zero_grad(set_to_none=False)
+        losses, _, _ = method(batch, student, teacher, None, dev, None, False, args)
+        losses["loss_cosine"].backward()
+        p = student.visual.blocks[1].mlp.w3.weight
+        norms.append((p.grad.double().norm().item(), student.visual.blocks[0].norm1.bias.grad.double().norm().item()))
+    for a, b in zip(norms[0], norms[1]):
+        assert abs(a - b) <= 1e-3 * a, norms
+    for a, b in zip(norms[0], norms[2]):
+        assert abs(a - b) <= 1e-3 * a, norms
