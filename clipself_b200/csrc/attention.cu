@@ -532,6 +532,7 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 namespace cs {
 int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
                      cudaStream_t st);
+int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
 }
 
 extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
@@ -548,6 +549,11 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
         CS_CHECK_ARG(row_stats == nullptr, "cs_attention_fwd: row_stats is only produced by the N <= 224 kernel");
+        // EXPERIMENTAL long-sequence tcgen05 kernel (attention_tc_long.cu): opt-in until validated on hardware
+        if (!legacy && getenv("CS_ATTN_LONG_TC") != nullptr) {
+            const int rc = attention_fwd_tc_long(qkv_bf16, B, N, H, scale, out_bf16, lse, (cudaStream_t)stream);
+            if (rc != CS_ERR_UNSUPPORTED) return rc;
+        }
     }
     const long long blocks = (long long)B * H * ceil_div(N, BQ);
     CS_CHECK_ARG(blocks < (1ll << 31), "cs_attention_fwd: grid too large");

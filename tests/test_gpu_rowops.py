@@ -1,4 +1,6 @@
 """LayerNorm / im2col / attention kernels against PyTorch fp32 references."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -101,3 +103,26 @@ def test_resize_bilinear(dev, hin, hout, dtype):
         torch.testing.assert_close(y.float(), ref.float(), rtol=8e-3, atol=1e-6)   # 1 bf16 ulp
     if hin == hout:
         assert torch.equal(y, x)
+
+
+@pytest.mark.skipif(os.environ.get("CS_TEST_EXPERIMENTAL") is None,
+                    reason="experimental long-sequence tcgen05 attention: opt-in (CS_TEST_EXPERIMENTAL=1), "
+                           "run it in its own process under `timeout`")
+@pytest.mark.parametrize("B,N,H", [(1, 225, 1), (2, 577, 16), (1, 1000, 2), (1, 4097, 12), (3, 129, 2)])
+def test_attention_fwd_long_tc(dev, B, N, H, monkeypatch):
+    from clipself_b200 import ops
+    monkeypatch.setenv("CS_ATTN_LONG_TC", "1")
+    D = H * 64
+    torch.manual_seed(7 * N + H)
+    qkv = torch.randn(B * N, 3 * D, device=dev).to(torch.bfloat16)
+    out = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=dev)
+    ops.attention_fwd(qkv, B, N, H, 0.125, out, lse)
+    torch.cuda.synchronize()
+    q, k, v = (t.reshape(B, N, H, 64).permute(0, 2, 1, 3) for t in qkv.float().view(B, N, 3, D).unbind(2))
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+    err = (out.float() - ref).abs().max().item()
+    print(f"long tc attention B={B} N={N} H={H}: max err {err:.4e}")
+    assert err < 2e-2
+    torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=1e-3)

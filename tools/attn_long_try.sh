@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round-2 starting point: validate the experimental long-sequence tcgen05 attention forward on a B200
+# (own process, bounded by `timeout`; the kernel's mbarrier waits trap instead of hanging).
+#   gpurun --timeout 600 -- 'bash tools/attn_long_try.sh'
+cd "$(dirname "$0")/.."
+CS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_rowops.py -q -m gpu -k long_tc -x -s 2>&1 | tail -15
+echo "--- timing (B=256 crops, ViT-L heads) mma.sync vs tcgen05"
+for v in "" 1; do
+  CS_ATTN_LONG_TC=$v timeout 120 python tools/attn_one.py 256 577 16 2>&1 | tail -2
+done
