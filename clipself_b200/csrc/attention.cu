@@ -549,7 +549,7 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
         CS_CHECK_ARG(row_stats == nullptr, "cs_attention_fwd: row_stats is only produced by the N <= 224 kernel");
-        // EXPERIMENTAL long-sequence tcgen05 kernel (attention_tc_long.cu): opt-in until validated on hardware
+        // EXPERIMENTAL long-sequence tcgen05 kernel (attention_tc_long.cu): parity-validated, opt-in until timed
         if (!legacy && getenv("CS_ATTN_LONG_TC") != nullptr) {
             const int rc = attention_fwd_tc_long(qkv_bf16, B, N, H, scale, out_bf16, lse, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
