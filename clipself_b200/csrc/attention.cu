@@ -532,7 +532,8 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 namespace cs {
 int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
                      cudaStream_t st);
-int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
+int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
+                          cudaStream_t st);
 }
 
 extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
@@ -548,12 +549,12 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
             const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
-        CS_CHECK_ARG(row_stats == nullptr, "cs_attention_fwd: row_stats is only produced by the N <= 224 kernel");
         // EXPERIMENTAL long-sequence tcgen05 kernel (attention_tc_long.cu): parity-validated, opt-in until timed
         if (!legacy && getenv("CS_ATTN_LONG_TC") != nullptr) {
-            const int rc = attention_fwd_tc_long(qkv_bf16, B, N, H, scale, out_bf16, lse, (cudaStream_t)stream);
+            const int rc = attention_fwd_tc_long(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
+        CS_CHECK_ARG(row_stats == nullptr, "cs_attention_fwd: row_stats is only produced by the tcgen05 kernels");
     }
     const long long blocks = (long long)B * H * ceil_div(N, BQ);
     CS_CHECK_ARG(blocks < (1ll << 31), "cs_attention_fwd: grid too large");

@@ -54,6 +54,7 @@ struct Params {
     float scale_log2, scale;
     __nv_bfloat16* out;
     float* lse;
+    float* row_stats;   // optional [B*N, 2H, 2]: per (row, head, dim-half) sum and sum of squares of the f32 output
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -299,6 +300,20 @@ attention_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap map, const Para
                     pk.w = pack_bf16(o_run[8 * i + 6] * inv, o_run[8 * i + 7] * inv);
                     *reinterpret_cast<uint4*>(dst + 8 * i) = pk;
                 }
+                if (p.row_stats != nullptr) {                       // statistics for the folded inner_attn_ln
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float f = o_run[hh * 32 + i] * inv;
+                            s1 += f;
+                            s2 = fmaf(f, f, s2);
+                        }
+                        *reinterpret_cast<float2*>(p.row_stats + (((long long)b * p.N + row) * (2 * p.H) + 2 * h + hh) * 2) =
+                            make_float2(s1, s2);
+                    }
+                }
                 if (p.lse != nullptr) p.lse[((long long)b * p.H + h) * p.N + row] = m_run * p.scale + logf(l_run);
             }
             c0 += p.nkb;
@@ -313,7 +328,8 @@ attention_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap map, const Para
 
 // Long-sequence tcgen05 forward.  Returns CS_ERR_UNSUPPORTED when the shape is outside the kernel's envelope
 // (cs_attention_fwd then falls through to the mma.sync kernel).
-int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st) {
+int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
+                          cudaStream_t st) {
     using namespace attn_tcl;
     if (N < 1) return CS_ERR_UNSUPPORTED;
     const int D = H * HD;
@@ -331,6 +347,7 @@ int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, voi
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
+    p.row_stats = row_stats;
     const int smem = 4 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 2 * P_BYTES + 512 + 1024;   // + barriers, alignment
     static bool configured = false;
     if (!configured) {

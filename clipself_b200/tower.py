@@ -66,6 +66,12 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _attention_emits_stats(tokens: int) -> bool:
+    """The LayerNorm row statistics come from the tcgen05 attention epilogues: the N <= 224 kernel, or the
+    (opt-in, CS_ATTN_LONG_TC) long-sequence kernel."""
+    return tokens <= 224 or os.environ.get("CS_ATTN_LONG_TC") is not None
+
+
 def chunk_schedule(rows: int, step: int) -> List[tuple]:
     """(start, count) pieces of a teacher pass over `rows` crops: a short first and second piece (step/4,
     step/2) so the pass can start as soon as the first few crops have crossed PCIe, then full `step`s."""
@@ -231,7 +237,7 @@ class TowerEngine:
         self.scale = cfg.head_dim ** -0.5
         # LayerNorm folding needs the producers' row statistics: the tcgen05 attention kernel (N <= 224)
         # and an even number of SwiGLU tiles per row
-        self.fold_proj = cfg.tokens <= 224 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+        self.fold_proj = _attention_emits_stats(cfg.tokens) and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
         self.fold_w3 = (cfg.hidden_pad // 128) % 2 == 0 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
 
         self._views: Dict[int, "TowerEngine"] = {}
@@ -259,7 +265,7 @@ class TowerEngine:
             v.w.pos = rescale_pos_embed(self.w.pos_src, grid)
             v.chunk_images = max(1, self.chunk_images * self.cfg.tokens // cfg.tokens)
             v._ws = None
-            v.fold_proj = cfg.tokens <= 224 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+            v.fold_proj = _attention_emits_stats(cfg.tokens) and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
             v.fold_w3 = self.fold_w3
             v._views = {}
             self._views[grid] = v
