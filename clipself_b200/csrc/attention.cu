@@ -534,6 +534,8 @@ int attention_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* ou
                      cudaStream_t st);
 int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
                           cudaStream_t st);
+int attention_bwd_tc(const void* qkv, const void* d_out, const float* lse, const float* delta, int B, int N, int H,
+                     float scale, const float* rope_cos, const float* rope_sin, void* dqkv, cudaStream_t st);
 }
 
 extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
@@ -587,6 +589,11 @@ extern "C" int cs_attention_bwd(const void* qkv_bf16, const void* out_bf16, cons
     attn_delta_kernel<<<ceil_div(rows * H, 8), 256, 0, st>>>((const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16,
                                                              rows, N, H, delta_ws);
     CS_LAUNCH_CHECK();
+    // EXPERIMENTAL tcgen05 backward (attention_bwd_tc.cu): staged for round 2, opt-in until validated on hardware
+    if (getenv("CS_ATTN_BWD_TC") != nullptr) {
+        const int rc = attention_bwd_tc(qkv_bf16, d_out_bf16, lse, delta_ws, B, N, H, scale, rope_cos, rope_sin, dqkv_bf16, st);
+        if (rc != CS_ERR_UNSUPPORTED) return rc;
+    }
     attention_bwd_dq_kernel<<<(unsigned)blocks, THREADS, BWD_SMEM, st>>>(
         (const __nv_bfloat16*)qkv_bf16, (const __nv_bfloat16*)d_out_bf16, lse, delta_ws, N, H, scale, rope_cos, rope_sin,
         (__nv_bfloat16*)dqkv_bf16);
