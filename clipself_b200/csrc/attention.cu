@@ -547,7 +547,9 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
     {
         // tcgen05 kernel for N <= 224 (B/16: 197 tokens); longer sequences use the streaming kernel below
         static const bool legacy = getenv("CS_ATTN_LEGACY") != nullptr;
-        if (!legacy) {
+        // CS_ATTN_FORCE_LONG (with CS_ATTN_LONG_TC): route short sequences through the long-sequence kernel too
+        // (round-2 experiment: its ping-pong schedule against the single-pass kernel at N = 197)
+        if (!legacy && getenv("CS_ATTN_FORCE_LONG") == nullptr) {
             const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
