@@ -302,7 +302,7 @@ def _oracle_step(O, ocfg, ssd, tsd, batch, backward):
     out = O.clipself_step(ssd, tsd, *batch, ocfg)
     if backward:
         out["loss"].backward()
-    return float(out["loss"])
+    return float(out["loss"].detach())
 
 
 def cpu_baseline(cfg_name, budget_s):
