@@ -68,3 +68,41 @@ class SyntheticDistillDataset(Dataset):
         crops = torch.randn(self.K, 3, self.crop_size, self.crop_size, generator=g)
         boxes = synthetic_boxes(self.K, self.kind, g, self.ragged)
         return image, boxes, crops
+
+
+class SyntheticEvalDataset(Dataset):
+    """Synthetic stand-in for COCOPanopticDataset (training/data.py:284-387): yields
+    (image [3,S,S], boxes [K,8] = (x0,y0,x1,y1, class, valid, box_size, is_thing), image_crops [K,3,s,s],
+    gt_masks [K, S/df, S/df] = the boxes rasterised at the feature-map resolution, masked_image_crops) and carries
+    the class embeddings (`--embed-path`) as `.embeddings` [classes, C]."""
+
+    def __init__(self, image_size: int, crop_size: int, max_boxes: int, num_classes: int, embed_dim: int,
+                 downsample_factor: int = 16, length: int = 64, seed: int = 0):
+        self.S, self.s, self.K, self.ncls, self.df = image_size, crop_size, max_boxes, num_classes, downsample_factor
+        self.length, self.seed = length, seed
+        g = torch.Generator().manual_seed(seed)
+        self.embeddings = torch.randn(num_classes, embed_dim, generator=g).numpy()
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + idx + 1)
+        image = torch.randn(3, self.S, self.S, generator=g)
+        crops = torch.randn(self.K, 3, self.s, self.s, generator=g)
+        b = synthetic_boxes(self.K, "proposal", g, ragged=True)               # [K,5]: box + valid
+        boxes = torch.zeros(self.K, 8)
+        boxes[:, :4] = b[:, :4]
+        boxes[:, 4] = torch.randint(0, self.ncls, (self.K,), generator=g).float()
+        boxes[:, 5] = b[:, 4]
+        boxes[:, 6] = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]) * self.S * self.S
+        boxes[:, 7] = (torch.rand(self.K, generator=g) > 0.4).float()
+        boxes[b[:, 4] < 0.5] = 0.0
+        m = self.S // self.df
+        masks = torch.zeros(self.K, m, m)
+        for k in range(self.K):
+            if boxes[k, 5] > 0.5:
+                x0, y0, x1, y1 = (boxes[k, :4] * m).tolist()
+                xa, ya = int(x0), int(y0)
+                masks[k, ya:max(int(-(-y1 // 1)), ya + 1), xa:max(int(-(-x1 // 1)), xa + 1)] = 1.0
+        return image, boxes, crops, masks, crops.clone()

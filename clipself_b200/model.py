@@ -374,6 +374,24 @@ class EVAVisionTransformer(nn.Module):
         fmap = self.encode_dense(x, keep_shape=False).contiguous()
         return ops.mask_pool_fwd(fmap, flat_masks, offsets)
 
+    def roi_and_mask_features(self, x: Tensor, normed_boxes: Sequence[Tensor], masks: Sequence[Tensor],
+                              normalize: bool = True):
+        """RoIAlign features and mask-pooled features of the same boxes from one dense map
+        (eva_vit_model.py:625-629 + 645-653 on a single encode_dense)."""
+        if self._needs_grad():
+            raise NotImplementedError("roi_and_mask_features is an inference path: call it under torch.no_grad()")
+        x = self._prep(x)
+        rois, offsets, R = self._pack_boxes(normed_boxes, x.device)
+        assert [int(m.shape[0]) for m in masks] == [int(b.shape[0]) for b in normed_boxes], "one mask per box"
+        dense = self._infer_engine(x).encode_dense_nograd(x)                       # [B,h,w,C]
+        B, h, w, C = dense.shape
+        roi = ops.roi_align_fwd(dense, rois, offsets, R)[0]
+        flat_masks = torch.cat([m.float().flatten(-2, -1) for m in masks]).to(x.device).contiguous()
+        pooled = ops.mask_pool_fwd(dense.view(B, h * w, C), flat_masks, offsets)
+        if normalize:
+            roi, pooled = ops.l2norm_fwd(roi)[0], ops.l2norm_fwd(pooled)[0]
+        return roi, pooled
+
 
 # ----------------------------------------------------------------------------------------------
 # CustomCLIP
@@ -435,3 +453,8 @@ class CustomCLIP(nn.Module):
     def encode_masks(self, image, masks, normalize=True, mask_attn=False):
         pooled = self.visual.mask_pool(image, masks)
         return self._normalize(pooled) if normalize else pooled
+
+    def encode_boxes_and_masks(self, image, normed_boxes, masks, normalize: bool = True):
+        """encode_pseudo_boxes + encode_masks on ONE dense pass (the reference's eval loop, zero_shot.py:71-77,
+        runs the tower twice for the same images).  Inference only."""
+        return self.visual.roi_and_mask_features(image, normed_boxes, masks, normalize)

@@ -26,6 +26,7 @@ from torch.utils.data.distributed import DistributedSampler
 from ..data import SyntheticDistillDataset
 from ..factory import create_model
 from ..optim import FusedAdamW
+from .zero_shot import zero_shot_eval
 from .clipself import CLIPSelf
 from .params import parse_args
 
@@ -88,6 +89,14 @@ def main(argv=None):
         if args.distributed else None
     loader = DataLoader(dataset, batch_size=args.batch_size, shuffle=sampler is None, sampler=sampler,
                         num_workers=args.workers, pin_memory=True, drop_last=True)
+    val_loader = None
+    if args.synthetic_eval_classes > 0:
+        from ..data import SyntheticEvalDataset
+        args.device = device
+        val_set = SyntheticEvalDataset(args.det_image_size, args.input_size, args.max_boxes, args.synthetic_eval_classes,
+                                       model.embed_dim, args.downsample_factor, length=max(args.batch_size * 2, 8),
+                                       seed=args.seed + 17)
+        val_loader = DataLoader(val_set, batch_size=args.batch_size, shuffle=False, num_workers=0, pin_memory=True)
     steps_per_epoch = args.train_steps_per_epoch or len(loader)
     total_steps = steps_per_epoch * args.epochs
     scheduler = cosine_lr(args.lr, args.warmup, total_steps)
@@ -114,7 +123,12 @@ def main(argv=None):
             if not args.skip_scheduler:
                 for g in optimizer.param_groups:
                     g["lr"] = scheduler(step)
-            optimizer.step()
+            grad_scale = 1.0
+            if args.grad_clip_norm is not None:                    # train.py:107-114 (clip_grad_norm_, L2)
+                eng = model.visual._student
+                span = eng.flat_grad[eng.layout.decay_start(eng.first_trainable):eng.layout.n_grad]
+                grad_scale = min(1.0, args.grad_clip_norm / (float(torch.linalg.vector_norm(span)) + 1e-6))
+            optimizer.step(grad_scale=grad_scale)                  # the clip factor is applied inside the fused update
             with torch.no_grad():                                  # train.py:118-119
                 model.logit_scale.clamp_(0, math.log(100))
             step += 1
@@ -135,6 +149,12 @@ def main(argv=None):
             torch.save({"epoch": epoch + 1, "name": args.name, "state_dict": {k: v.cpu() for k, v in sd.items()},
                         "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()}},
                        os.path.join(out_dir, f"epoch_{epoch + 1}.pt"))
+        if val_loader is not None:                                 # train.py:168-187 -> zero_shot.py:172-193
+            model.eval()
+            metrics = zero_shot_eval(model, {"val": val_loader}, epoch + 1, args)
+            model.train()
+            if rank == 0 and metrics:
+                logging.info(f"Eval Epoch: {epoch + 1} " + ", ".join(f"{k}: {v:.4f}" for k, v in metrics.items()))
     if args.distributed:
         dist.destroy_process_group()
 

@@ -64,6 +64,10 @@ def parse_args(args=None):
     p.add_argument("--crop-scale", type=float, default=1.0)
     p.add_argument("--train-steps-per-epoch", type=int, default=0,
                    help="synthetic_distill only: optimizer steps per epoch (0 = dataset length / global batch)")
+    p.add_argument("--synthetic-eval-classes", type=int, default=0,
+                   help="synthetic_distill only: > 0 runs the region-classification eval loop (zero_shot.py) on a "
+                        "synthetic panoptic-style set with this many classes every --zeroshot-frequency epochs")
+    p.add_argument("--image-ave-pool", action="store_true", default=False)
     p.add_argument("--fused-optimizer", action="store_true", default=True)
     args = p.parse_args(args)
     for name, val in get_default_params(args.model).items():

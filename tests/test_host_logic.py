@@ -188,3 +188,69 @@ def test_flat_layout_trainable_suffix_ranges():
                 continue
             inside = ds <= o < lay.n_decay or ns <= o < lay.n_grad
             assert inside == (int(name.split(".")[1]) >= k), (k, name)
+
+
+def test_zero_shot_macc_matches_hand_computation():
+    """macc_with_is_thing (zero_shot.py:135-169): per-class mean of top-1 / top-5 hits, thing and stuff apart."""
+    from clipself_b200.training.zero_shot import macc_with_is_thing
+    # 6 boxes: classes 0,0,2 are 'thing', 1,1,3 'stuff'; columns = top-5 hit matrix (at most one 1 per row)
+    correct = torch.tensor([[1, 0, 0, 0, 0], [0, 0, 1, 0, 0], [0, 0, 0, 0, 0],
+                            [0, 1, 0, 0, 0], [1, 0, 0, 0, 0], [0, 0, 0, 0, 1]], dtype=torch.float32)
+    labels = torch.tensor([0, 0, 2, 1, 1, 3])
+    is_thing = torch.tensor([1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
+    r = macc_with_is_thing(correct, is_thing, labels, "rois")
+    assert r["rois.thing.macc1"] == pytest.approx((0.5 + 0.0) / 2)          # class 0: 1/2, class 2: 0/1
+    assert r["rois.thing.macc5"] == pytest.approx((1.0 + 0.0) / 2)
+    assert r["rois.stuff.macc1"] == pytest.approx((0.5 + 0.0) / 2)          # class 1: 1/2, class 3: 0/1
+    assert r["rois.stuff.macc5"] == pytest.approx((1.0 + 1.0) / 2)
+
+
+def test_zero_shot_run_with_a_stub_model():
+    """The loop's bookkeeping (valid filtering, image-major order, top-5 / similarity extraction) with a stub
+    model whose features are the class embeddings of the ground-truth labels: every box must be a top-1 hit."""
+    import types
+    from torch.utils.data import DataLoader
+    from clipself_b200.data import SyntheticEvalDataset
+    from clipself_b200.training import zero_shot
+
+    ds = SyntheticEvalDataset(image_size=32, crop_size=16, max_boxes=5, num_classes=7, embed_dim=12, length=6, seed=3)
+    emb = torch.nn.functional.normalize(torch.from_numpy(ds.embeddings).float(), dim=-1)
+
+    class Stub:
+        def __init__(self):
+            self.labels = None
+            self.visual = self
+
+        def encode_boxes_and_masks(self, images, rois, masks, normalize=True):
+            assert [r.shape[0] for r in rois] == [m.shape[0] for m in masks]
+            n = sum(r.shape[0] for r in rois)
+            lab = self.pending[:n]
+            return emb[lab], emb[(lab + 1) % 7]                  # RoI features right, mask-pooled features wrong
+
+        def encode_image(self, crops, normalize=True):
+            return emb[self.pending[:crops.shape[0]]]
+
+    stub = Stub()
+    loader = DataLoader(ds, batch_size=3)
+    # labels in the order the loop visits them
+    order = []
+    for _, bboxes, _, _, _ in loader:
+        for b in bboxes:
+            order.append(b[b[:, 5] > 0.5, 4].long())
+    per_batch = [torch.cat(order[i:i + 3]) for i in range(0, len(order), 3)]
+
+    class Feed:
+        def __iter__(self_inner):
+            for batch, lab in zip(loader, per_batch):
+                stub.pending = lab
+                yield batch
+        dataset = ds
+
+    args = types.SimpleNamespace(device="cpu", distributed=False, image_ave_pool=False)
+    c_rois, c_crops, c_mask, s_rois, s_crops, s_mask, sizes, is_thing, labels = zero_shot.run(stub, Feed(), args)
+    n = sum(x.numel() for x in per_batch)
+    assert c_rois.shape == (n, 5) and labels.tolist() == torch.cat(per_batch).tolist()
+    assert c_rois[:, 0].sum() == n and c_crops[:, 0].sum() == n           # always the top-1 hit
+    assert c_mask[:, 0].sum() == 0                                         # never top-1 for the shifted labels
+    torch.testing.assert_close(s_rois, torch.ones(n), atol=1e-5, rtol=0)
+    assert sizes.shape == (n,) and is_thing.shape == (n,)
