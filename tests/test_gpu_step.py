@@ -300,3 +300,33 @@ def test_repeated_backward_does_not_double_gradients():
         assert abs(a - b) <= 1e-3 * a, norms
     for a, b in zip(norms[0], norms[2]):
         assert abs(a - b) <= 1e-3 * a, norms
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CS_TEST_EXPERIMENTAL") is None,
+                    reason="added after the round-1 GPU budget was spent: opt-in until it has run once (CS_TEST_EXPERIMENTAL=1)")
+def test_eval_loop_shared_dense_pass(golden):
+    """encode_boxes_and_masks == (encode_pseudo_boxes, encode_masks), and the region-classification loop runs."""
+    import types as _t
+    from torch.utils.data import DataLoader
+    from clipself_b200.data import SyntheticEvalDataset
+    from clipself_b200.training import zero_shot
+    g = golden("tiny_ragged")
+    ocfg, B, K, kind, ragged = CASES["tiny_ragged"]
+    dev = torch.device("cuda")
+    m = build_model(ocfg, int(g["seed"]), dev).eval()
+    images, boxes, _ = O.synth_batch(ocfg, B, K, int(g["seed"]) + 2, kind=kind, ragged=ragged)
+    rois = [b[b[:, -1] > 0.5, :4].to(dev) for b in boxes]
+    masks = [t.to(dev) for t in torch.split(torch.from_numpy(g["masks"]), [r.shape[0] for r in rois])]
+    with torch.no_grad():
+        f, mp = m.encode_boxes_and_masks(images.to(dev), rois, masks, normalize=True)
+        f2 = m.encode_pseudo_boxes(images.to(dev), rois, normalize=True)
+        mp2 = m.encode_masks(images.to(dev), masks, normalize=True)
+    torch.testing.assert_close(f, f2, rtol=0, atol=1e-6)
+    torch.testing.assert_close(mp, mp2, rtol=0, atol=1e-6)
+    assert rel(f.cpu().numpy(), g["student_roi_normalized"]) < 1.5e-2
+    ds = SyntheticEvalDataset(ocfg.image_size, ocfg.image_size, 4, num_classes=6, embed_dim=ocfg.embed_dim,
+                              downsample_factor=ocfg.patch, length=6, seed=1)
+    args = _t.SimpleNamespace(device=dev, distributed=False, image_ave_pool=False, zeroshot_frequency=1, epochs=1)
+    res = zero_shot.zero_shot_eval(m, {"val": DataLoader(ds, batch_size=3)}, 1, args)
+    assert set(res) == {f"{p}.{t}.macc{k}" for p in ("rois", "crops", "maskpool") for t in ("thing", "stuff") for k in (1, 5)}
+    assert all(0.0 <= v <= 1.0 for v in res.values())

@@ -13,3 +13,5 @@ timeout 120 python tools/attn_one.py 256 197 12 2>&1 | tail -1
 CS_ATTN_LONG_TC=1 CS_ATTN_FORCE_LONG=1 timeout 120 python tools/attn_one.py 256 197 12 2>&1 | tail -1
 echo "--- staged tcgen05 backward (never run before): parity of dq / dk / dv against fp32 autograd"
 CS_ATTN_BWD_TC=1 timeout 300 python -m pytest tests/test_gpu_backward_kernels.py -q -m gpu -k attention_bwd -x -s 2>&1 | tail -15
+echo "--- eval loop / shared dense pass (added after the round-1 GPU budget ended)"
+CS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_step.py -q -m gpu -k eval_loop -x -s 2>&1 | tail -8
