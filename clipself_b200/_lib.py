@@ -39,6 +39,9 @@ PROTOTYPES = {
     "cs_cosine_loss_bwd": [vp, vp, vp, i32, i32, f32, vp, vp, vp],
     "cs_l2norm_fwd": [vp, i64, i32, vp, vp, vp],
     "cs_l2norm_bwd": [vp, vp, vp, i64, i32, vp, vp],
+    "cs_crop_workspace_bytes": [i32, i32, i32, i32, C.POINTER(C.c_int64)],
+    "cs_crop_resize_normalize": [vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
+                                 i64, vp],
     "cs_im2col_patches": [vp, i32, i32, i32, i32, vp, i64, vp],
     "cs_resize_bilinear": [vp, i32, i64, i32, i32, i32, i32, vp, vp],
     "cs_fill_cls_rows": [vp, vp, i32, i32, i32, vp, vp],

@@ -1,0 +1,73 @@
+"""Host side of the on-device crop generation (STAGED, see csrc/crops.cu): turns the pixel boxes of
+GridDistillDataset._obtain_image_crops (training/data.py:226-245) into the integer crop descriptors the kernels
+consume, with exactly the rounding of the reference's CPU path:
+
+  Image.crop(box)           -> x0,y0,x1,y1 = int(round(v))            (Python round: half to even)
+  ResizeMaxSize(s) / ResizeLongest(S)  (open_clip/transform.py:26-49, 169-191)
+                            -> scale = s / float(max(h, w)); new = round(side * scale); centre / top-left padding
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+OPENAI_DATASET_MEAN = (0.48145466, 0.4578275, 0.40821073)      # open_clip/constants.py
+OPENAI_DATASET_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def crop_descriptors(boxes_px: np.ndarray, size: int, center: bool = True) -> Tuple[np.ndarray, int, int]:
+    """boxes_px [K,4] float (x0,y0,x1,y1 in source pixels) -> (descs int32 [K,8], ksize_max, tmp_rows_max).
+    descs rows = (x0, y0, x1, y1, out_w, out_h, pad_left, pad_top); degenerate boxes get out_w = out_h = 0."""
+    b = np.rint(np.asarray(boxes_px, np.float64)).astype(np.int64).reshape(-1, 4)       # np.rint: half to even
+    w, h = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+    ok = (w > 0) & (h > 0)
+    longest = np.maximum(np.maximum(w, h), 1).astype(np.float64)
+    scale = size / longest
+    out_h = np.where(ok, np.rint(h * scale), 0).astype(np.int64)
+    out_w = np.where(ok, np.rint(w * scale), 0).astype(np.int64)
+    pad_h, pad_w = size - out_h, size - out_w
+    top, left = (pad_h // 2, pad_w // 2) if center else (np.zeros_like(pad_h), np.zeros_like(pad_w))
+    descs = np.stack([b[:, 0], b[:, 1], b[:, 2], b[:, 3], out_w, out_h, np.where(ok, left, 0), np.where(ok, top, 0)],
+                     axis=1).astype(np.int32)
+    ratio = 1.0
+    if ok.any():
+        ratio = max(1.0, float(np.max(w[ok] / np.maximum(out_w[ok], 1))), float(np.max(h[ok] / np.maximum(out_h[ok], 1))))
+    ksize_max = int(math.ceil(2.0 * ratio)) * 2 + 1
+    tmp_rows_max = int(h[ok].max()) if ok.any() else 0
+    return np.ascontiguousarray(descs), ksize_max, tmp_rows_max
+
+
+def device_crops(image_u8: torch.Tensor, boxes_px: Sequence[Sequence[float]], size: int, center: bool = True,
+                 mean=OPENAI_DATASET_MEAN, std=OPENAI_DATASET_STD) -> torch.Tensor:
+    """image_u8: uint8 [H,W,3] CUDA tensor (the decoded image); returns f32 [K,3,size,size] crops =
+    transforms[1](image.crop(box)) for every box, computed on the device."""
+    L.require_device()
+    assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.dim() == 3 and image_u8.shape[2] == 3
+    image_u8 = image_u8.contiguous()
+    H, W, _ = image_u8.shape
+    descs, ksize_max, tmp_rows_max = crop_descriptors(np.asarray(boxes_px, np.float64), size, center)
+    K = descs.shape[0]
+    dev = image_u8.device
+    out = torch.empty(K, 3, size, size, device=dev, dtype=torch.float32)
+    if K == 0:
+        return out
+    import ctypes as C
+    need = C.c_int64(0)
+    L.call("cs_crop_workspace_bytes", K, size, ksize_max, tmp_rows_max, C.byref(need))
+    ws = torch.empty(int(need.value), device=dev, dtype=torch.uint8)
+    d_descs = torch.from_numpy(descs).to(dev)
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    L.call("cs_crop_resize_normalize", image_u8.data_ptr(), H, W, d_descs.data_ptr(), K, size, ksize_max, tmp_rows_max,
+           m3, s3, out.data_ptr(), ws.data_ptr(), int(need.value), torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def device_det_image(image_u8: torch.Tensor, det_size: int, mean=OPENAI_DATASET_MEAN, std=OPENAI_DATASET_STD) -> torch.Tensor:
+    """The student's input: det_image_transform = ResizeLongest(det_size) + ToTensor + Normalize -> f32 [3,S,S]."""
+    H, W, _ = image_u8.shape
+    return device_crops(image_u8, [[0.0, 0.0, float(W), float(H)]], det_size, center=False, mean=mean, std=std)[0]

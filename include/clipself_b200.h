@@ -96,6 +96,28 @@ int cs_l2norm_bwd(const float* y, const float* inv_norm, const float* d_y, int64
                   float* d_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Crop generation (STAGED: not yet run on hardware, see csrc/crops.cu) — replaces the CPU PIL path of
+ * GridDistillDataset._obtain_image_crops (training/data.py:226-245: image.crop(box) -> transforms[1]) and
+ * the transforms of open_clip/transform.py:26-49,119-133 (ResizeMaxSize, centre pad) / :136-191
+ * (ResizeLongest, pad right/bottom), bit-exact with Pillow's bicubic ImagingResample.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t x0, y0, x1, y1;      /* source rectangle, pixels (Image.crop's rounded box; outside the image = 0) */
+    int32_t out_w, out_h;        /* size after the bicubic resize (round(side * max_size / longest side))        */
+    int32_t pad_left, pad_top;   /* where the resized crop sits inside the size x size zero canvas               */
+} cs_crop_desc_t;
+
+/* bytes of scratch cs_crop_resize_normalize needs: coefficient tables + the uint8 intermediate of the
+ * horizontal pass; ksize_max >= 2*ceil(2*max(in/out,1))+1 over all crops and axes, tmp_rows_max >= max crop height. */
+int cs_crop_workspace_bytes(int K, int size, int ksize_max, int tmp_rows_max, int64_t* bytes);
+
+/* image_hwc: uint8 [H,W,3] on the device; descs: K cs_crop_desc_t on the device; mean3 / std3: host floats;
+ * out: f32 [K,3,size,size] = Normalize(ToTensor(pad(resize(crop)))). */
+int cs_crop_resize_normalize(const uint8_t* image_hwc, int H, int W, const void* descs, int K, int size,
+                             int ksize_max, int tmp_rows_max, const float* mean3, const float* std3, float* out,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tower kernels (EVA02 ViT, eva_vit_model.py)
  * ---------------------------------------------------------------------------------------- */
 

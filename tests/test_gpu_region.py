@@ -151,3 +151,22 @@ def test_mask_pool_empty_mask_and_large_extract(dev):
     R = int(offsets[-1])
     assert R == idx_ref.numel() and torch.equal(rois[:R].cpu(), torch.cat(rois_ref))
     assert crop_index[:R].cpu().tolist() == idx_ref.tolist()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CS_TEST_EXPERIMENTAL") is None,
+                    reason="staged on-device crop generation: its arithmetic is verified on the CPU "
+                           "(tests/test_crops_emulation.py); the kernels themselves have not run yet (CS_TEST_EXPERIMENTAL=1)")
+def test_device_crops_bit_exact_vs_reference_fixture(dev, golden):
+    import numpy as np
+    from clipself_b200.crops import device_crops, device_det_image
+    from oracle import crops_oracle as CO
+    g = golden("crops_small")
+    img = torch.from_numpy(g["image"]).to(dev)
+    got = device_crops(img, g["boxes"], int(g["size"]))
+    assert np.array_equal(got.cpu().numpy(), g["crops"])                    # bit-exact f32
+    assert np.array_equal(device_det_image(img, int(g["det_size"])).cpu().numpy(), g["det"])
+    g2 = golden("crops_coco_like")
+    img2 = torch.from_numpy(g2["image"]).to(dev)
+    got2 = device_crops(img2, g2["boxes"], int(g2["size"])).cpu().numpy()
+    ref2 = np.stack([CO.image_crop(g2["image"], b, int(g2["size"])) for b in g2["boxes"]])
+    assert np.array_equal(got2, ref2)

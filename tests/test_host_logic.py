@@ -254,3 +254,32 @@ def test_zero_shot_run_with_a_stub_model():
     assert c_mask[:, 0].sum() == 0                                         # never top-1 for the shifted labels
     torch.testing.assert_close(s_rois, torch.ones(n), atol=1e-5, rtol=0)
     assert sizes.shape == (n,) and is_thing.shape == (n,)
+
+
+def test_crop_descriptors_match_the_oracle_rounding():
+    """Host half of the on-device crop generation: rectangles, resized sizes, padding and the scratch bounds must
+    agree with the oracle's restatement of Image.crop / ResizeMaxSize / ResizeLongest for every box."""
+    import math
+    import numpy as np
+    from clipself_b200.crops import crop_descriptors
+    from oracle import crops_oracle as C
+    rng = np.random.default_rng(11)
+    boxes = np.concatenate([rng.random((200, 2)) * [600, 400], rng.random((200, 2)) * [600, 400]], 1)
+    boxes = np.concatenate([np.minimum(boxes[:, :2], boxes[:, 2:]), np.maximum(boxes[:, :2], boxes[:, 2:]) + 1.3], 1)
+    boxes[:5] = [[0.5, 1.5, 20.5, 30.5], [2.5, 3.5, 10.49, 12.51], [0, 0, 640, 480], [10, 10, 10.2, 300], [5, 5, 6, 6]]
+    for size, center in ((224, True), (32, True), (1024, False)):
+        descs, ksize_max, rows_max = crop_descriptors(boxes, size, center)
+        for b, d in zip(boxes, descs):
+            rect = C.crop_box_to_rect(b)
+            assert tuple(d[:4]) == rect
+            w, h = rect[2] - rect[0], rect[3] - rect[1]
+            if w <= 0 or h <= 0:
+                assert d[4] == 0 and d[5] == 0
+                continue
+            nh, nw = C.resized_size(h, w, size)
+            assert (d[5], d[4]) == (nh, nw)
+            assert (d[6], d[7]) == (((size - nw) // 2, (size - nh) // 2) if center else (0, 0))
+            for n_in, n_out in ((w, nw), (h, nh)):
+                if n_out > 0:
+                    assert C.precompute_coeffs(n_in, 0.0, float(n_in), n_out)[2] <= ksize_max
+            assert h <= rows_max

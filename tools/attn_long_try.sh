@@ -15,3 +15,5 @@ echo "--- staged tcgen05 backward (never run before): parity of dq / dk / dv aga
 CS_ATTN_BWD_TC=1 timeout 300 python -m pytest tests/test_gpu_backward_kernels.py -q -m gpu -k attention_bwd -x -s 2>&1 | tail -15
 echo "--- eval loop / shared dense pass (added after the round-1 GPU budget ended)"
 CS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_step.py -q -m gpu -k eval_loop -x -s 2>&1 | tail -8
+echo "--- staged on-device crop generation (bit-exact vs the reference-transform fixtures)"
+CS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_region.py -q -m gpu -k device_crops -x -s 2>&1 | tail -8
