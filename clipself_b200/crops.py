@@ -71,3 +71,48 @@ def device_det_image(image_u8: torch.Tensor, det_size: int, mean=OPENAI_DATASET_
     """The student's input: det_image_transform = ResizeLongest(det_size) + ToTensor + Normalize -> f32 [3,S,S]."""
     H, W, _ = image_u8.shape
     return device_crops(image_u8, [[0.0, 0.0, float(W), float(H)]], det_size, center=False, mean=mean, std=std)[0]
+
+
+def grid_choices(max_split: int = 16):
+    """GridDistillDataset._init_choices (training/data.py:200-205): the (M, N) grids a sample is drawn from."""
+    return [(m, n) for m in range(1, max_split + 1) for n in range((m + 1) // 2, min(m * 2 + 1, max_split + 1))]
+
+
+def grid_distill_sample(image_u8: torch.Tensor, choice: Tuple[int, int], indices: Sequence[int], max_anns: int,
+                        det_size: int, crop_size: int, crop_scale: float = 1.0, crops_fn=None, det_fn=None):
+    """One training sample of GridDistillDataset (training/data.py:226-281) from a decoded uint8 [H,W,3] image:
+    `indices` is the shuffled order of the M*N grid cells (the dataset draws it with random.shuffle; the caller owns
+    the RNG), the first `max_anns` are used.  Returns (image f32 [3,S,S], boxes_template [max_anns,5],
+    image_crops_template [max_anns,3,s,s]) — the batch contract of the CLIPSelf plug-in.  The pixels are produced
+    by device_crops / device_det_image (crops_fn / det_fn are injection points for the CPU tests)."""
+    from .data import grid_box_templates
+    crops_fn = crops_fn or device_crops
+    det_fn = det_fn or device_det_image
+    img_h, img_w = int(image_u8.shape[0]), int(image_u8.shape[1])
+    M, N = choice
+    normed = grid_box_templates(M, N)                                          # [M*N,4] f32, row-major (data.py:207-224)
+    idx = list(indices)[:max_anns]
+    boxes = normed * torch.tensor([img_w, img_h, img_w, img_h])                # f32 * int64 -> f32, as in the reference
+    px = []
+    for i in idx:
+        x0, y0, x1, y1 = boxes[i].tolist()
+        if crop_scale > 1.0:                                                   # data.py:236-241
+            box_w, box_h = x1 - x0, y1 - y0
+            cx, cy = (x1 + x0) / 2, (y1 + y0) / 2
+            delta = 0.5 * crop_scale
+            x0, y0, x1, y1 = max(cx - box_w * delta, 0), max(cy - box_h * delta, 0), \
+                min(cx + box_w * delta, img_w), min(cy + box_h * delta, img_h)
+        px.append([x0, y0, x1, y1])
+    crops = crops_fn(image_u8, px, crop_size)
+    new_image = det_fn(image_u8, det_size)
+    scale = min(det_size / img_h, det_size / img_w)                            # transform.py:193-207 get_scale
+    sel = boxes[idx].clone()
+    sel[:, :4] *= scale
+    sel[:, [0, 2]] /= det_size
+    sel[:, [1, 3]] /= det_size
+    boxes_template = torch.zeros(max_anns, 5)
+    crops_template = torch.zeros(max_anns, 3, crop_size, crop_size, device=crops.device)
+    boxes_template[:len(idx), :4] = sel
+    boxes_template[:len(idx), 4] = 1.0
+    crops_template[:len(idx)] = crops
+    return new_image, boxes_template, crops_template

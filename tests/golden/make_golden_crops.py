@@ -55,6 +55,52 @@ def run(tag, h, w, size, det_size, seed, n_boxes, store_full):
     print(tag, crops.shape, det.shape, "->", path, f"{os.path.getsize(path) / 1e3:.1f} kB")
 
 
+def run_grid_sample(tag, h, w, crop_size, det_size, max_anns, choice, seed, crop_scale=1.0):
+    """One sample exactly as GridDistillDataset produces it (training/data.py:200-281): the class's own
+    _init_boxes / _obtain_image_crops run on a stand-in `self` (the constructor needs COCO annotation files),
+    followed by the box re-normalisation lines of __getitem__ (:270-281) copied in spirit below."""
+    import random
+    import types
+    # import-only stand-ins for the annotation libraries (absent here; never called)
+    for name in ("pycocotools", "pycocotools.coco", "pycocotools.cocoeval", "pycocotools.mask", "panopticapi", "panopticapi.utils"):
+        m = sys.modules.setdefault(name, types.ModuleType(name))
+        m.__path__ = []
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["pycocotools.cocoeval"].COCOeval = object
+    for sub in ("coco", "cocoeval", "mask"):
+        setattr(sys.modules["pycocotools"], sub, sys.modules["pycocotools." + sub])
+    sys.modules["panopticapi"].utils = sys.modules["panopticapi.utils"]
+    from open_clip.transform import get_scale
+    from training.data import GridDistillDataset
+    img = synth_image(h, w, seed)
+    pil = Image.fromarray(img)
+    me = types.SimpleNamespace(transforms=(det_image_transform(det_size, is_train=False),
+                                           image_transform(crop_size, is_train=False, resize_longest_max=True)),
+                               max_anns=max_anns, args=types.SimpleNamespace(crop_scale=crop_scale), choices=[choice])
+    GridDistillDataset._init_boxes(me)
+    random.seed(seed)
+    image_crops, boxes = GridDistillDataset._obtain_image_crops(me, pil, choice)
+    new_image = me.transforms[0](pil)
+    scale = get_scale(pil, new_image)
+    boxes_template = torch.zeros(max_anns, 4 + 1)
+    crops_template = torch.zeros(max_anns, 3, crop_size, crop_size)
+    _, nh, nw = new_image.shape
+    boxes[:, :4] *= scale
+    boxes[:, [0, 2]] /= nw
+    boxes[:, [1, 3]] /= nh
+    boxes_template[:boxes.shape[0], :4] = boxes
+    boxes_template[:boxes.shape[0], 4] = 1.0
+    crops_template[:boxes.shape[0]] = image_crops
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, image=img, choice=np.array(choice), seed=np.int64(seed), max_anns=np.int64(max_anns),
+                        crop_size=np.int64(crop_size), det_size=np.int64(det_size), crop_scale=np.float64(crop_scale),
+                        new_image=new_image.numpy(), boxes_template=boxes_template.numpy(), crops_template=crops_template.numpy())
+    print(tag, tuple(new_image.shape), tuple(boxes_template.shape), "->", path, f"{os.path.getsize(path) / 1e3:.1f} kB")
+
+
 if __name__ == "__main__":
+    run_grid_sample("grid_sample_small", h=90, w=120, crop_size=32, det_size=64, max_anns=5, choice=(2, 3), seed=700)
+    run_grid_sample("grid_sample_scaled", h=75, w=50, crop_size=32, det_size=64, max_anns=8, choice=(3, 2), seed=701,
+                    crop_scale=1.5)
     run("crops_small", h=97, w=131, size=32, det_size=48, seed=600, n_boxes=6, store_full=True)
     run("crops_coco_like", h=480, w=640, size=224, det_size=1024, seed=601, n_boxes=8, store_full=False)

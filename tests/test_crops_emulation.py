@@ -64,3 +64,32 @@ def test_emulation_matches_oracle_on_random_boxes(emul):
             else:
                 ref = O.image_crop(img, b, size)
             assert np.array_equal(o, ref), (b, size)
+
+
+@pytest.mark.parametrize("tag", ["grid_sample_small", "grid_sample_scaled"])
+def test_grid_distill_sample_matches_the_reference_dataset(emul, golden, tag):
+    """A whole GridDistillDataset sample (fixture produced by the reference's own _init_boxes / _obtain_image_crops
+    and transforms): grid boxes, shuffled selection, crop_scale, crops, detector image and the re-normalised boxes.
+    The pixels come from the kernels' host emulation, so this is the device path minus the launches."""
+    import random
+    import torch
+    from clipself_b200.crops import grid_distill_sample
+    g = golden(tag)
+    M, N = (int(v) for v in g["choice"])
+    random.seed(int(g["seed"]))
+    indices = list(range(M * N))
+    random.shuffle(indices)                                   # what _obtain_image_crops draws (data.py:230-232)
+    img = g["image"]
+
+    def crops_fn(image, boxes_px, size):
+        return torch.from_numpy(emul(img, np.asarray(boxes_px, np.float64), size, True))
+
+    def det_fn(image, size):
+        return torch.from_numpy(emul(img, np.array([[0.0, 0.0, img.shape[1], img.shape[0]]]), size, False)[0])
+
+    new_image, boxes_t, crops_t = grid_distill_sample(torch.from_numpy(img), (M, N), indices, int(g["max_anns"]),
+                                                      int(g["det_size"]), int(g["crop_size"]), float(g["crop_scale"]),
+                                                      crops_fn=crops_fn, det_fn=det_fn)
+    assert np.array_equal(new_image.numpy(), g["new_image"])
+    assert np.array_equal(boxes_t.numpy(), g["boxes_template"])               # bit-exact f32 boxes
+    assert np.array_equal(crops_t.numpy(), g["crops_template"])
