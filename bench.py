@@ -305,15 +305,35 @@ def _oracle_step(O, ocfg, ssd, tsd, batch, backward):
     return float(out["loss"].detach())
 
 
+def pick_threads(fn):
+    """The CPU arm should use the host as well as it can: time one call at 16, 32, 64 and all hardware threads
+    (many-core hosts are often slower with every thread than with a few dozen: small fp32 GEMMs, NUMA) and keep
+    the fastest setting.  Stops early once a larger count is clearly slower.  Returns (threads, {count: seconds})."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({min(n, ncpu) for n in (16, 32, 64, ncpu)})
+    seen, best_n, best_t = {}, cands[0], float("inf")
+    for n in cands:
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        seen[n] = round(dt, 3)
+        if dt < best_t:
+            best_n, best_t = n, dt
+        elif dt > 1.5 * best_t:
+            break
+    torch.set_num_threads(best_n)
+    return best_n, seen
+
+
 def cpu_baseline(cfg_name, budget_s):
     """Oracle port on the host cores, BASELINE.json configs[0] shape (2 images x 8 boxes, fwd+loss)."""
     from oracle import clipself_oracle as O
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     ocfg = O.CFG_B16
     ssd, tsd = O.synth_tower_weights(ocfg, 1), O.synth_tower_weights(ocfg, 2)
     batch = O.synth_batch(ocfg, 2, 8, 3, kind="grid")
     with torch.no_grad():
+        threads, sweep = pick_threads(lambda: _oracle_step(O, ocfg, ssd, tsd, batch, False))
         times = []
         t_end = time.perf_counter() + budget_s
         while len(times) < 2 or (time.perf_counter() < t_end and len(times) < 10):
@@ -324,7 +344,8 @@ def cpu_baseline(cfg_name, budget_s):
                 break
     best = min(times)
     return {"value": round(2 / best, 3), "unit": "images/sec", "cores": threads, "kind": "port",
-            "sample": f"oracle port (torch fp32 CPU), EVA02-B/16, 2 images x 8 boxes, forward+loss, min of {len(times)} reps"}
+            "sample": f"oracle port (torch fp32 CPU), EVA02-B/16, 2 images x 8 boxes, forward+loss, min of {len(times)} reps, "
+                      f"{threads} threads (thread sweep, s per call: {sweep})"}
 
 
 def run_reference(args):
@@ -336,8 +357,6 @@ def run_reference(args):
     from oracle import clipself_oracle as O
     wl = WORKLOADS[args.workload]
     K = wl["boxes"]
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     ocfg = O.CFG_B16
     ssd, tsd = O.synth_tower_weights(ocfg, 1), O.synth_tower_weights(ocfg, 2)
     for k, v in ssd.items():
@@ -345,8 +364,7 @@ def run_reference(args):
             v.requires_grad_(True)
     batch = O.synth_batch(ocfg, 1, K, 3, kind=wl["kind"])
     warm = min(args.warmup, 1) if args.warmup else 0
-    for _ in range(max(warm, 1)):
-        _oracle_step(O, ocfg, ssd, tsd, batch, True)
+    threads, sweep = pick_threads(lambda: _oracle_step(O, ocfg, ssd, tsd, batch, True))    # doubles as the warm-up
     t0 = time.perf_counter()
     steps = 0
     for _ in range(args.steps):
@@ -358,7 +376,7 @@ def run_reference(args):
     value = 1.0 / dt
     world = int(os.environ.get("WORLD_SIZE", "1"))
     sample = (f"oracle port (torch fp32 CPU, {threads} threads): 1 image x {K} boxes per step, "
-              f"teacher fwd + student fwd+bwd, {steps} steps timed")
+              f"teacher fwd + student fwd+bwd, {steps} steps timed; thread sweep (s per step): {sweep}")
     out = {"impl": "reference", "metric": "images/sec (32 boxes/img) ViT-B/16@224 distill step", "value": round(value, 4),
            "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": max(warm, 1),
            "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
