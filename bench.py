@@ -307,8 +307,9 @@ def _oracle_step(O, ocfg, ssd, tsd, batch, backward):
 
 def pick_threads(fn):
     """The CPU arm should use the host as well as it can: time one call at 16, 32 and 64 threads (capped at the
-    hardware thread count) and keep the fastest setting.  Every thread of a 128-thread host was measured 10-60x
-    SLOWER than a few dozen on this workload (small fp32 GEMMs, NUMA), so counts above 64 are not tried.
+    hardware thread count) and keep the fastest setting.  With all 128 threads of the GPU box this workload ran at
+    0.03 images/s in round 1 against 1.9 images/s on an 8-core container (small fp32 GEMMs, NUMA), so counts above
+    64 are not tried.
     Stops early once a larger count is clearly slower.  Returns (threads, {count: seconds})."""
     ncpu = os.cpu_count() or 1
     cands = sorted({min(n, ncpu) for n in (16, 32, 64)})
