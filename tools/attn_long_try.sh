@@ -5,11 +5,10 @@
 cd "$(dirname "$0")/.."
 CS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_rowops.py -q -m gpu -k long_tc -x -s 2>&1 | tail -15
 echo "--- timing (B=256 crops, ViT-L heads) mma.sync vs tcgen05"
-for v in "" 1; do
-  CS_ATTN_LONG_TC=$v timeout 120 python tools/attn_one.py 256 577 16 2>&1 | tail -2
-done
+env -u CS_ATTN_LONG_TC timeout 120 python tools/attn_one.py 256 577 16 2>&1 | tail -1
+CS_ATTN_LONG_TC=1 timeout 120 python tools/attn_one.py 256 577 16 2>&1 | tail -1
 echo "--- the teacher's shape (256 crops x 197 tokens x 12 heads): single-pass kernel vs the ping-pong long kernel"
-timeout 120 python tools/attn_one.py 256 197 12 2>&1 | tail -1
+env -u CS_ATTN_LONG_TC -u CS_ATTN_FORCE_LONG timeout 120 python tools/attn_one.py 256 197 12 2>&1 | tail -1
 CS_ATTN_LONG_TC=1 CS_ATTN_FORCE_LONG=1 timeout 120 python tools/attn_one.py 256 197 12 2>&1 | tail -1
 echo "--- staged tcgen05 backward (never run before): parity of dq / dk / dv against fp32 autograd"
 CS_ATTN_BWD_TC=1 timeout 300 python -m pytest tests/test_gpu_backward_kernels.py -q -m gpu -k attention_bwd -x -s 2>&1 | tail -15
