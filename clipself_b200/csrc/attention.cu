@@ -538,6 +538,12 @@ int attention_bwd_tc(const void* qkv, const void* d_out, const float* lse, const
                      float scale, const float* rope_cos, const float* rope_sin, void* dqkv, cudaStream_t st);
 }
 
+// opt-in switch: set and neither empty nor "0"
+static bool env_on(const char* name) {
+    const char* v = getenv(name);
+    return v != nullptr && v[0] != '\0' && !(v[0] == '0' && v[1] == '\0');
+}
+
 extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,
                                 float* lse, float* row_stats, void* stream) {
     using namespace cs;
@@ -546,15 +552,15 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
     CS_CHECK_ARG(B > 0 && N > 0 && H > 0, "cs_attention_fwd: bad shape");
     {
         // tcgen05 kernel for N <= 224 (B/16: 197 tokens); longer sequences use the streaming kernel below
-        static const bool legacy = getenv("CS_ATTN_LEGACY") != nullptr;
+        static const bool legacy = env_on("CS_ATTN_LEGACY");
         // CS_ATTN_FORCE_LONG (with CS_ATTN_LONG_TC): route short sequences through the long-sequence kernel too
         // (round-2 experiment: its ping-pong schedule against the single-pass kernel at N = 197)
-        if (!legacy && getenv("CS_ATTN_FORCE_LONG") == nullptr) {
+        if (!legacy && !env_on("CS_ATTN_FORCE_LONG")) {
             const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
         // EXPERIMENTAL long-sequence tcgen05 kernel (attention_tc_long.cu): parity-validated, opt-in until timed
-        if (!legacy && getenv("CS_ATTN_LONG_TC") != nullptr) {
+        if (!legacy && env_on("CS_ATTN_LONG_TC")) {
             const int rc = attention_fwd_tc_long(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
@@ -592,7 +598,7 @@ extern "C" int cs_attention_bwd(const void* qkv_bf16, const void* out_bf16, cons
                                                              rows, N, H, delta_ws);
     CS_LAUNCH_CHECK();
     // EXPERIMENTAL tcgen05 backward (attention_bwd_tc.cu): staged for round 2, opt-in until validated on hardware
-    if (getenv("CS_ATTN_BWD_TC") != nullptr) {
+    if (env_on("CS_ATTN_BWD_TC")) {
         const int rc = attention_bwd_tc(qkv_bf16, d_out_bf16, lse, delta_ws, B, N, H, scale, rope_cos, rope_sin, dqkv_bf16, st);
         if (rc != CS_ERR_UNSUPPORTED) return rc;
     }

@@ -69,7 +69,7 @@ def _round_up(x: int, m: int) -> int:
 def _attention_emits_stats(tokens: int) -> bool:
     """The LayerNorm row statistics come from the tcgen05 attention epilogues: the N <= 224 kernel, or the
     (opt-in, CS_ATTN_LONG_TC) long-sequence kernel."""
-    return tokens <= 224 or os.environ.get("CS_ATTN_LONG_TC") is not None
+    return tokens <= 224 or os.environ.get("CS_ATTN_LONG_TC", "0") not in ("", "0")
 
 
 def chunk_schedule(rows: int, step: int) -> List[tuple]:
