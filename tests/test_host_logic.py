@@ -283,3 +283,25 @@ def test_crop_descriptors_match_the_oracle_rounding():
                 if n_out > 0:
                     assert C.precompute_coeffs(n_in, 0.0, float(n_in), n_out)[2] <= ksize_max
             assert h <= rows_max
+
+
+def test_barrier_protocols_of_the_staged_attention_kernels():
+    """tools/mbar_sim.py replays the mbarrier traffic of attention_bwd_tc.cu / attention_tc_long.cu under random
+    schedules with asynchronous TMA / tcgen05.commit completions: no deadlock, no buffer overwritten while in use."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mbar_sim", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "tools", "mbar_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for seed in range(6):
+        for items, nblk in [(1, 1), (2, 3), (3, 10)]:
+            sim.sim_bwd(seed, items, nblk, dkv=False)
+            sim.sim_bwd(seed, items, nblk, dkv=True)
+            sim.sim_fwd_long(seed, items, nblk)
+    # the model notices a protocol slip: a barrier sized for 32 of the 33 arrivals of the dKV producer warp
+    import types
+    with pytest.raises(AssertionError):
+        s = sim.Sim(0)
+        s.bar("b", 32)
+        s.bars["b"].arrive(33)
