@@ -77,6 +77,23 @@ def main(argv=None):
     args.input_size = model.visual.image_size
     if args.lock_image:
         model.lock_image_tower(unlocked_groups=args.lock_image_unlocked_groups)
+    # optionally resume (main.py:216-235): a train checkpoint {epoch, state_dict, optimizer} continues at its epoch
+    # (the optimizer moments are restored when the fused optimizer is created after the first forward); a bare
+    # state_dict is loaded for fine-tuning / evaluation.  `text.*` keys are not on this path and are skipped.
+    start_epoch, resume_opt = 0, None
+    if args.resume:
+        ckpt = torch.load(args.resume, map_location="cpu")
+        sd = ckpt["state_dict"] if "epoch" in ckpt else ckpt
+        if next(iter(sd)).startswith("module"):
+            sd = {k[len("module."):]: v for k, v in sd.items()}
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        bad = [k for k in list(missing) + list(unexpected) if not (k.startswith("text.") or "rope" in k)]
+        if bad:
+            raise RuntimeError(f"--resume {args.resume}: state_dict mismatch on {bad[:8]}")
+        if "epoch" in ckpt:
+            start_epoch, resume_opt = int(ckpt["epoch"]), ckpt.get("optimizer")
+        if rank == 0:
+            logging.info(f"=> resuming checkpoint '{args.resume}' (epoch {start_epoch})")
     model.train()
     dist_model.eval()
     method = CLIPSelf()
@@ -102,8 +119,8 @@ def main(argv=None):
     scheduler = cosine_lr(args.lr, args.warmup, total_steps)
 
     optimizer = None
-    step = 0
-    for epoch in range(args.epochs):
+    step = start_epoch * steps_per_epoch
+    for epoch in range(start_epoch, args.epochs):
         if sampler is not None:
             sampler.set_epoch(epoch)
         t_last = time.time()
@@ -120,6 +137,8 @@ def main(argv=None):
             if optimizer is None:                                  # engine exists after the first forward
                 optimizer = FusedAdamW(model.visual._student, lr=args.lr, betas=(args.beta1, args.beta2),
                                        eps=args.eps, weight_decay=args.wd)
+                if resume_opt is not None:
+                    optimizer.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in resume_opt.items()})
             if not args.skip_scheduler:
                 for g in optimizer.param_groups:
                     g["lr"] = scheduler(step)
