@@ -305,3 +305,17 @@ def test_barrier_protocols_of_the_staged_attention_kernels():
         s = sim.Sim(0)
         s.bar("b", 32)
         s.bars["b"].arrive(33)
+
+
+def test_staged_attention_backward_dataflow_reproduces_autograd():
+    """tools/attn_bwd_emul.py replays the operand table / masks / accumulator-to-section mapping / inverse RoPE of
+    csrc/attention_bwd_tc.cu in numpy (tensor-core products as matmuls) and compares with torch autograd."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("attn_bwd_emul", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "tools", "attn_bwd_emul.py"))
+    emul = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emul)
+    for case in [(2, 17, 2, True), (2, 64, 1, False), (1, 130, 1, False)]:
+        res = emul.check(*case)
+        assert all(v < 2e-2 for v in res.values()), (case, res)
