@@ -290,7 +290,7 @@ def run_b200(args):
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": len(prof),
                      "gemm_share_of_step": round(gemm_ms / ms_step, 3)},
-        "cpu_baseline": cpu_baseline(cfg_name=wl["model"], budget_s=25.0),
+        "cpu_baseline": None if args.no_cpu else cpu_baseline(cfg_name=wl["model"], budget_s=25.0),
     }
     print(json.dumps(out), flush=True)
     if distributed:
@@ -397,6 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="development runs: skip the cpu_baseline leg (null in the JSON line)")
     ap.add_argument("--profile-one-step", action="store_true", help="run 1 warm-up + 1 step between cudaProfilerStart/Stop")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -37,15 +37,39 @@ def load_state_dict(checkpoint_path: str, map_location="cpu", model_key="model|m
     return state_dict
 
 
+def resize_evaclip_pos_embed(state_dict, model, interpolation: str = "bicubic", seq_dim=1):
+    """eva_clip/utils.py:78-106: when the checkpoint's token grid differs from the model's, bicubically resample the
+    patch-position rows of `visual.pos_embed` (CLS row kept) and, as the reference does in the same branch, resample
+    `visual.patch_embed.proj.weight` to the model's patch size.  In place on `state_dict`."""
+    if "visual.pos_embed" not in state_dict:
+        return
+    pos = state_dict["visual.pos_embed"]
+    emb = pos.shape[-1]
+    num_patches = model.visual.patch_embed.num_patches
+    num_extra = model.visual.pos_embed.shape[-2] - num_patches
+    orig_size = int((pos.shape[-2] - num_extra) ** 0.5)
+    new_size = int(num_patches ** 0.5)
+    if orig_size == new_size:
+        return
+    logging.info("Position interpolate from %dx%d to %dx%d" % (orig_size, orig_size, new_size, new_size))
+    extra = pos[:, :num_extra]
+    tok = pos[:, num_extra:].reshape(-1, orig_size, orig_size, emb).permute(0, 3, 1, 2)
+    tok = torch.nn.functional.interpolate(tok.float(), size=(new_size, new_size), mode="bicubic", align_corners=False)
+    state_dict["visual.pos_embed"] = torch.cat((extra, tok.permute(0, 2, 3, 1).flatten(1, 2).to(pos.dtype)), dim=1)
+    w = state_dict["visual.patch_embed.proj.weight"]
+    state_dict["visual.patch_embed.proj.weight"] = torch.nn.functional.interpolate(
+        w.float(), size=model.visual.patch_embed.patch_size, mode="bicubic", align_corners=False)
+
+
 def load_checkpoint(model, checkpoint_path, model_key="model|module|state_dict", strict=False):
+    """eva_clip/factory.py:110-129 for EVA checkpoints (`visual.pos_embed` branch)."""
     state_dict = load_state_dict(checkpoint_path, model_key=model_key)
-    pe = state_dict.get("visual.pos_embed")
-    if pe is not None and pe.shape != model.visual.pos_embed.shape:
-        raise NotImplementedError("positional-embedding resize at load time (eva_clip/utils.py:78-106) is part of the "
-                                  "variable-resolution row, SURVEY.md §8f rank 4")
-    # text tower keys are kept out of the module (not on the path) but must not make the load fail
-    incompatible = model.load_state_dict({k: v for k, v in state_dict.items() if not k.startswith("text.")},
-                                         strict=False)
+    if "text.logit_scale" in state_dict and hasattr(model, "logit_scale"):
+        state_dict["logit_scale"] = state_dict.pop("text.logit_scale")
+    resize_evaclip_pos_embed(state_dict, model)
+    if model.text is None:           # towers built without a text_cfg hold no text.* entries
+        state_dict = {k: v for k, v in state_dict.items() if not k.startswith("text.")}
+    incompatible = model.load_state_dict(state_dict, strict=strict)
     logging.info(f"incompatible_keys.missing_keys: {incompatible.missing_keys}")
     return incompatible
 
@@ -70,11 +94,23 @@ def create_model(
         raise NotImplementedError("jit=True is an OpenAI-checkpoint path, not used by CLIPSelf")
     cfg = get_model_config(model_name)                      # RuntimeError for unknown names, like the reference
     if force_image_size is not None:
-        raise NotImplementedError("force_image_size needs the variable-resolution tower (SURVEY.md §8f rank 4)")
+        # eva_clip/factory.py:263-265: override the tower's native resolution; a checkpoint's pos_embed is then
+        # resampled at load (resize_evaclip_pos_embed)
+        size = force_image_size[0] if isinstance(force_image_size, (tuple, list)) else int(force_image_size)
+        if size % cfg["vision_cfg"]["patch_size"] != 0:
+            raise ValueError(f"force_image_size={size} is not a multiple of the patch size {cfg['vision_cfg']['patch_size']}")
+        cfg["vision_cfg"]["image_size"] = size
     if precision in ("bf16", "fp16", "pure_bf16", "pure_fp16"):
         # the reference's pure-bf16 mode dies at torchvision RoIAlign; the runnable
         # bf16 mode is amp_bf16 = f32 master weights + bf16 tensor-core operands, which is what we run.
         raise NotImplementedError(f"precision={precision!r}: use 'amp_bf16' (f32 master weights, bf16 tensor cores)")
+    if precision == "fp32" and not getattr(create_model, "_warned_fp32", False):
+        # the reference's precision argument only selects the WEIGHT dtype here (eva_clip/factory.py:342-344); the
+        # arithmetic is chosen by the caller's autocast context.  This library has one arithmetic: say so once.
+        logging.warning("clipself_b200: weights are kept in fp32 (precision='fp32'), but every contraction runs on the "
+                        "tensor cores with bf16 operands and fp32 accumulation (the reference's amp_bf16 arithmetic); "
+                        "there is no fp32-operand path")
+        create_model._warned_fp32 = True
     model = CustomCLIP(embed_dim=cfg["embed_dim"], vision_cfg=cfg["vision_cfg"], text_cfg=cfg["text_cfg"])
     if pretrained and pretrained != "eva":
         raise RuntimeError(f"Pretrained weights ({pretrained}) not found for model {model_name}.")

@@ -292,7 +292,10 @@ class EVAVisionTransformer(nn.Module):
 
     def _infer_engine_native(self) -> TowerEngine:
         self._check_cuda()
-        version = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        # weights_epoch: the fused optimizer updates the flat parameter buffer through the C ABI, which neither bumps
+        # `_version` nor moves `data_ptr` — FusedAdamW.step() counts its updates on the engine instead
+        version = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters()) + \
+            (self._student.weights_epoch if self._student is not None else 0,)
         if self._infer is None or version != self._infer_version:
             if self._infer is None:
                 self._infer = TowerEngine(self.cfg, self._tower_sd(), self._device())
@@ -396,6 +399,50 @@ class EVAVisionTransformer(nn.Module):
 # ----------------------------------------------------------------------------------------------
 # CustomCLIP
 # ----------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    """A node of the opaque text-tower parameter tree (no forward)."""
+
+
+def text_param_shapes(text_cfg: dict, embed_dim: int):
+    """Names and shapes of the reference's `text.*` state_dict entries (TextTransformer,
+    eva_clip/transformer.py:642-742; 149 keys for both EVA02-CLIP configs)."""
+    W, L, ctx, vocab = text_cfg["width"], text_cfg["layers"], text_cfg["context_length"], text_cfg["vocab_size"]
+    out = [("positional_embedding", (ctx, W)), ("text_projection", (W, embed_dim)), ("token_embedding.weight", (vocab, W))]
+    for i in range(L):
+        p = f"transformer.resblocks.{i}."
+        out += [(p + "ln_1.weight", (W,)), (p + "ln_1.bias", (W,)), (p + "attn.in_proj_weight", (3 * W, W)),
+                (p + "attn.in_proj_bias", (3 * W,)), (p + "attn.out_proj.weight", (W, W)), (p + "attn.out_proj.bias", (W,)),
+                (p + "ln_2.weight", (W,)), (p + "ln_2.bias", (W,)), (p + "mlp.c_fc.weight", (4 * W, W)),
+                (p + "mlp.c_fc.bias", (4 * W,)), (p + "mlp.c_proj.weight", (W, 4 * W)), (p + "mlp.c_proj.bias", (W,))]
+    out += [("ln_final.weight", (W,)), ("ln_final.bias", (W,))]
+    return out
+
+
+def _opaque_text_tower(text_cfg: dict, embed_dim: int) -> nn.Module:
+    """The frozen text tower as a parameter tree with the reference's key names and shapes.  It is never executed
+    on the CLIPSelf path (clipself.py:7-49 touches `visual` only); holding its tensors lets checkpoints round-trip
+    all 436 keys (main.py:300-317 saves `model.state_dict()`, eva_clip/factory.py:110-129 / `--resume` load it back,
+    strictly in the `--resume` case)."""
+    root = _Holder()
+    for name, shape in text_param_shapes(text_cfg, embed_dim):
+        parts = name.split(".")
+        node = root
+        for part in parts[:-1]:
+            if not hasattr(node, part):
+                node.add_module(part, _Holder())
+            node = getattr(node, part)
+        t = torch.empty(shape)
+        leaf = parts[-1]
+        if leaf == "bias" or leaf.endswith("_bias"):
+            nn.init.zeros_(t)
+        elif len(shape) == 1:
+            nn.init.ones_(t)
+        else:
+            nn.init.normal_(t, std=0.02 if "embedding" in name else shape[-1] ** -0.5)
+        node.register_parameter(leaf, nn.Parameter(t, requires_grad=False))
+    return root
+
+
 class CustomCLIP(nn.Module):
     """API surface of eva_clip/model.py:272-346.  The text tower is not on the CLIPSelf path
     (frozen and never executed there); it is kept as an opaque parameter holder so checkpoints
@@ -409,8 +456,9 @@ class CustomCLIP(nn.Module):
             img_size=v["image_size"], patch_size=v["patch_size"], num_classes=embed_dim, embed_dim=width,
             depth=v["layers"], num_heads=width // v.get("head_width", 64), mlp_ratio=v.get("mlp_ratio", 4.0),
             pt_hw_seq_len=v.get("pt_hw_seq_len", 16))
-        self.text = None
         self.text_cfg = dict(text_cfg) if text_cfg else None
+        # with a text_cfg: the reference's 149 `text.*` entries as frozen, never-executed parameters
+        self.text = _opaque_text_tower(self.text_cfg, embed_dim) if self.text_cfg else None
         self.embed_dim = embed_dim
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
 

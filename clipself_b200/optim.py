@@ -41,6 +41,7 @@ class FusedAdamW:
                        g_decay["lr"], b1, b2, self.eps, g_decay["weight_decay"], self.step_count, grad_scale)
         ops.adamw_step(e.flat_param[ns:ng], e.flat_grad[ns:ng], self.exp_avg[ns:ng], self.exp_avg_sq[ns:ng],
                        g_nodecay["lr"], b1, b2, self.eps, g_nodecay["weight_decay"], self.step_count, grad_scale)
+        e.weights_epoch += 1         # invalidates forward-only packs built from these weights (model.py: _infer_engine_native)
 
     def state_dict(self):
         return dict(exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, step=self.step_count,

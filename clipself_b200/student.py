@@ -219,6 +219,7 @@ class StudentEngine:
         # blocks[:first_trainable] are frozen (lock_image_tower(unlocked_groups=n) unfreezes blocks[-n:],
         # eva_vit_model.py:500-516): no gradient, no all-reduce, no optimizer update for them
         self.first_trainable = 0
+        self.weights_epoch = 0          # bumped by FusedAdamW.step(): in-place updates through the C ABI are invisible to torch
         self.repack()
 
     # ------------------------------------------------------------------ packing

@@ -47,6 +47,66 @@ def student_teacher_ensemble(student_sd, teacher_sd, alpha):
             for k, v in student_sd.items()}
 
 
+class LossScaler:
+    """The `torch.cuda.amp.GradScaler` protocol the reference runs under `--precision amp` (main.py:214,
+    train.py:46-50 `scaler.scale(loss).backward()`, :98-111 unscale / clip / `scaler.step` / `scaler.update`):
+    dynamic loss scale (init 2^16, x2 after 2000 clean steps, x0.5 and the optimizer step SKIPPED when a
+    gradient is inf/nan), `state_dict()` with torch's key names so `checkpoint['scaler']` round-trips
+    (main.py:311-312, :231-232).  The unscale is folded into the fused AdamW's gradient factor.  The tensor-core
+    operands stay bf16 (this library has no fp16 kernels); the protocol, the skipped steps and the checkpoint
+    entry are the reference's."""
+
+    def __init__(self, init_scale=2.0 ** 16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.scale_value, self.growth_factor, self.backoff_factor = float(init_scale), growth_factor, backoff_factor
+        self.growth_interval, self.growth_tracker, self.found_inf = growth_interval, 0, False
+
+    def scale(self, loss):
+        return loss * self.scale_value
+
+    def check(self, flat_grad_span) -> bool:
+        """True when every gradient is finite (one reduction + a host read, like GradScaler's found_inf)."""
+        self.found_inf = not bool(torch.isfinite(flat_grad_span.sum()))
+        return not self.found_inf
+
+    def update(self):
+        if self.found_inf:
+            self.scale_value *= self.backoff_factor
+            self.growth_tracker = 0
+        else:
+            self.growth_tracker += 1
+            if self.growth_tracker == self.growth_interval:
+                self.scale_value *= self.growth_factor
+                self.growth_tracker = 0
+
+    def state_dict(self):
+        return {"scale": self.scale_value, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": self.growth_tracker}
+
+    def load_state_dict(self, sd):
+        self.scale_value, self.growth_factor = float(sd["scale"]), sd["growth_factor"]
+        self.backoff_factor, self.growth_interval = sd["backoff_factor"], sd["growth_interval"]
+        self.growth_tracker = int(sd["_growth_tracker"])
+
+
+LATEST_CHECKPOINT_NAME = "epoch_latest.pt"        # main.py:40
+
+
+def save_checkpoints(args, checkpoint_dict, completed_epoch, out_dir):
+    """main.py:300-328: epoch_N.pt at the last epoch or every --save-frequency epochs, optional removal of the
+    previous one, and --save-most-recent through tmp.pt + os.replace so a failed save cannot corrupt the latest."""
+    os.makedirs(out_dir, exist_ok=True)
+    if completed_epoch == args.epochs or (args.save_frequency > 0 and completed_epoch % args.save_frequency == 0):
+        torch.save(checkpoint_dict, os.path.join(out_dir, f"epoch_{completed_epoch}.pt"))
+    if args.delete_previous_checkpoint:
+        previous = os.path.join(out_dir, f"epoch_{completed_epoch - 1}.pt")
+        if os.path.exists(previous):
+            os.remove(previous)
+    if args.save_most_recent:
+        tmp, latest = os.path.join(out_dir, "tmp.pt"), os.path.join(out_dir, LATEST_CHECKPOINT_NAME)
+        torch.save(checkpoint_dict, tmp)
+        os.replace(tmp, latest)
+
+
 def main(argv=None):
     args = parse_args(argv)
     rank = int(os.environ.get("RANK", "0"))
@@ -61,6 +121,14 @@ def main(argv=None):
                         format="%(asctime)s | %(levelname)s | %(message)s")
     if args.precision in ("bf16", "fp16"):
         raise NotImplementedError("pure bf16/fp16 cannot run the reference path either (SURVEY fact 8): use amp_bf16")
+    if args.precision == "fp32":
+        raise NotImplementedError("--precision fp32: this library has no fp32-operand path (every contraction runs on "
+                                  "the tensor cores with bf16 operands, fp32 accumulation); use amp_bf16 or amp")
+    # precision.py:5-12 / main.py:214: `amp` = autocast + GradScaler, `amp_bf16` = bf16 autocast without a scaler
+    scaler = LossScaler() if args.precision == "amp" else None
+    if scaler is not None and rank == 0:
+        logging.warning("--precision amp: running the GradScaler protocol (dynamic loss scale, skipped steps on inf/nan, "
+                        "'scaler' in checkpoints) over bf16 tensor-core operands; there are no fp16 kernels in this library")
     if args.accum_freq != 1:
         raise AssertionError("accum_freq must be 1 (train.py:89)")
     if args.dataset_type != "synthetic_distill":
@@ -69,10 +137,15 @@ def main(argv=None):
 
     torch.manual_seed(args.seed)
     np.random.seed(args.seed)
-    cache = args.cache_dir if args.cache_dir and os.path.exists(args.cache_dir) else ""
+    # `--cache-dir` is the checkpoint path (scripts/*.sh); a path that does not exist raises inside create_model
+    # exactly like eva_clip/factory.py:290-295.  Random initialisation is an explicit opt-in: --cache-dir "".
+    cache = args.cache_dir or ""
     model = create_model(args.model, "eva", precision="amp_bf16", device=device, cache_dir=cache)
     dist_model = create_model(args.model, "eva", precision="amp_bf16", device=device, cache_dir=cache)
     if not cache:
+        if rank == 0:
+            logging.warning("--cache-dir '': RANDOM-INIT run; the teacher is a copy of the random student "
+                            "(synthetic benchmarking only: nothing is being distilled)")
         dist_model.load_state_dict(model.state_dict())          # random init: teacher = student copy
     args.input_size = model.visual.image_size
     if args.lock_image:
@@ -86,14 +159,19 @@ def main(argv=None):
         sd = ckpt["state_dict"] if "epoch" in ckpt else ckpt
         if next(iter(sd)).startswith("module"):
             sd = {k[len("module."):]: v for k, v in sd.items()}
-        missing, unexpected = model.load_state_dict(sd, strict=False)
-        bad = [k for k in list(missing) + list(unexpected) if not (k.startswith("text.") or "rope" in k)]
-        if bad:
-            raise RuntimeError(f"--resume {args.resume}: state_dict mismatch on {bad[:8]}")
+        model.load_state_dict(sd)                               # strict, like main.py:223-234
         if "epoch" in ckpt:
             start_epoch, resume_opt = int(ckpt["epoch"]), ckpt.get("optimizer")
+            if scaler is not None and "scaler" in ckpt:
+                scaler.load_state_dict(ckpt["scaler"])
         if rank == 0:
             logging.info(f"=> resuming checkpoint '{args.resume}' (epoch {start_epoch})")
+    trainable_outside_blocks = [n for n, p in model.named_parameters()
+                                if p.requires_grad and not n.startswith("visual.blocks.") and n != "logit_scale"]
+    if trainable_outside_blocks:
+        raise NotImplementedError(
+            "the fused training path updates visual.blocks.* only (what the reference's scripts train with --lock-image); "
+            f"these parameters would silently stay constant: {trainable_outside_blocks[:6]} — pass --lock-image")
     model.train()
     dist_model.eval()
     method = CLIPSelf()
@@ -123,7 +201,7 @@ def main(argv=None):
     for epoch in range(start_epoch, args.epochs):
         if sampler is not None:
             sampler.set_epoch(epoch)
-        t_last = time.time()
+        t_last, i_last = time.time(), -1
         it = iter(loader)
         for i in range(steps_per_epoch):
             try:
@@ -133,7 +211,7 @@ def main(argv=None):
                 batch = next(it)
             losses, batch_size, logit_scale = method(batch, model, dist_model, None, device, None, args.distributed, args)
             total_loss = sum(losses.values())
-            total_loss.backward()
+            (scaler.scale(total_loss) if scaler is not None else total_loss).backward()     # train.py:46-50
             if optimizer is None:                                  # engine exists after the first forward
                 optimizer = FusedAdamW(model.visual._student, lr=args.lr, betas=(args.beta1, args.beta2),
                                        eps=args.eps, weight_decay=args.wd)
@@ -142,33 +220,39 @@ def main(argv=None):
             if not args.skip_scheduler:
                 for g in optimizer.param_groups:
                     g["lr"] = scheduler(step)
-            grad_scale = 1.0
-            if args.grad_clip_norm is not None:                    # train.py:107-114 (clip_grad_norm_, L2)
-                eng = model.visual._student
-                span = eng.flat_grad[eng.layout.decay_start(eng.first_trainable):eng.layout.n_grad]
-                grad_scale = min(1.0, args.grad_clip_norm / (float(torch.linalg.vector_norm(span)) + 1e-6))
-            optimizer.step(grad_scale=grad_scale)                  # the clip factor is applied inside the fused update
+            eng = model.visual._student
+            span = eng.flat_grad[eng.layout.decay_start(eng.first_trainable):eng.layout.n_grad]
+            grad_scale = 1.0 / scaler.scale_value if scaler is not None else 1.0     # scaler.unscale_ (train.py:108)
+            finite = scaler.check(span) if scaler is not None else True
+            if finite and args.grad_clip_norm is not None:         # train.py:107-114 (clip_grad_norm_, L2, unscaled grads)
+                norm = float(torch.linalg.vector_norm(span)) * grad_scale
+                grad_scale *= min(1.0, args.grad_clip_norm / (norm + 1e-6))
+            if finite:
+                optimizer.step(grad_scale=grad_scale)              # unscale and clip factors applied inside the fused update
+            if scaler is not None:
+                scaler.update()                                    # train.py:111
             with torch.no_grad():                                  # train.py:118-119
                 model.logit_scale.clamp_(0, math.log(100))
             step += 1
             if rank == 0 and (i % args.log_every_n_steps == 0 or i == steps_per_epoch - 1):
                 loss_v = total_loss.item()
                 dt = time.time() - t_last
-                n = min(args.log_every_n_steps, i + 1) if i else 1
+                n = i - i_last                                     # steps since the previous log line
                 logging.info(f"Train Epoch: {epoch} [{i + 1}/{steps_per_epoch}] Loss: {loss_v:.5f} "
                              f"LR: {optimizer.param_groups[0]['lr']:.3e} Logit Scale: {logit_scale.item():.3f} "
                              f"{n * batch_size * world / max(dt, 1e-9):.1f} samples/s")
-                t_last = time.time()
-        if rank == 0 and args.name and (epoch + 1) % args.save_frequency == 0:
-            out_dir = os.path.join(args.logs, args.name, "checkpoints")
-            os.makedirs(out_dir, exist_ok=True)
+                t_last, i_last = time.time(), i
+        if rank == 0 and args.name:                                # main.py:280-328
             sd = model.state_dict()
             if args.alpha < 1.0:
                 sd = student_teacher_ensemble(sd, dist_model.state_dict(), args.alpha)
-            torch.save({"epoch": epoch + 1, "name": args.name, "state_dict": {k: v.cpu() for k, v in sd.items()},
-                        "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()}},
-                       os.path.join(out_dir, f"epoch_{epoch + 1}.pt"))
-        if val_loader is not None:                                 # train.py:168-187 -> zero_shot.py:172-193
+            checkpoint_dict = {"epoch": epoch + 1, "name": args.name, "state_dict": {k: v.cpu() for k, v in sd.items()},
+                               "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v)
+                                             for k, v in optimizer.state_dict().items()}}
+            if scaler is not None:
+                checkpoint_dict["scaler"] = scaler.state_dict()
+            save_checkpoints(args, checkpoint_dict, epoch + 1, os.path.join(args.logs, args.name, "checkpoints"))
+        if val_loader is not None:                                 # main.py:330 -> zero_shot.py:172-193 (frequency checked there)
             model.eval()
             metrics = zero_shot_eval(model, {"val": val_loader}, epoch + 1, args)
             model.train()

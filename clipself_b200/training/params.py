@@ -40,6 +40,8 @@ def parse_args(args=None):
     p.add_argument("--skip-scheduler", action="store_true", default=False)
     p.add_argument("--lr-scheduler", type=str, default="cosine")
     p.add_argument("--save-frequency", type=int, default=1)
+    p.add_argument("--save-most-recent", action="store_true", default=False)
+    p.add_argument("--delete-previous-checkpoint", action="store_true", default=False)
     p.add_argument("--zeroshot-frequency", type=int, default=2)
     p.add_argument("--resume", default=None, type=str)
     p.add_argument("--precision", choices=["amp", "amp_bf16", "amp_bfloat16", "bf16", "fp16", "fp32"], default="amp")
