@@ -23,13 +23,15 @@ class GemmEpilogue(C.Structure):
                 ("bias", vp), ("residual", vp), ("ldr", i64), ("rope_pos", vp), ("rope_freq", vp),
                 ("rope_grid", C.c_int32), ("tokens", C.c_int32), ("rope_cols", C.c_int32), ("pos_embed", vp),
                 ("alpha", f32), ("reserved", C.c_int32), ("ln_stats", vp), ("ln_c1", vp), ("ln_parts", C.c_int32),
-                ("ln_dim", C.c_int32), ("ln_eps", f32), ("reserved2", C.c_int32), ("stats_out", vp)]
+                ("ln_dim", C.c_int32), ("ln_eps", f32), ("reserved2", C.c_int32), ("stats_out", vp),
+                ("out2_bf16", vp), ("ldo2", i64)]
 
 
 # name -> argtypes, exactly the prototypes of include/clipself_b200.h
 PROTOTYPES = {
     "cs_abi_version": [],
     "cs_device_info": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)],
+    "cs_tensor_map_encodes": [],
     "cs_extract_rois": [vp, i32, i32, vp, vp, vp, vp, vp],
     "cs_gather_rows": [vp, vp, i32, i64, vp, vp],
     "cs_roi_align_fwd": [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp],
@@ -46,6 +48,7 @@ PROTOTYPES = {
     "cs_resize_bilinear": [vp, i32, i64, i32, i32, i32, i32, vp, vp],
     "cs_fill_cls_rows": [vp, vp, i32, i32, i32, vp, vp],
     "cs_layernorm_fwd": [vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, f32, vp, i64, vp, vp, vp],
+    "cs_row_stats_cast": [vp, i64, i64, i32, vp, i64, vp, i32, vp],
     "cs_gemm_bf16": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],
     "cs_pack_swiglu_weights": [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp],
     "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp, vp],
@@ -79,7 +82,7 @@ def lib() -> C.CDLL:
         l.cs_last_error.argtypes = []
         for name, args in PROTOTYPES.items():
             fn = getattr(l, name)          # AttributeError if the .so does not export it
-            fn.restype = C.c_int
+            fn.restype = C.c_int64 if name == "cs_tensor_map_encodes" else C.c_int
             fn.argtypes = args
         _lib = l
     return _lib

@@ -551,16 +551,15 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
     CS_CHECK_ARG(qkv_bf16 && out_bf16, "cs_attention_fwd: null pointer");
     CS_CHECK_ARG(B > 0 && N > 0 && H > 0, "cs_attention_fwd: bad shape");
     {
-        // tcgen05 kernel for N <= 224 (B/16: 197 tokens); longer sequences use the streaming kernel below
+        // tcgen05 kernels: the single-pass kernel for N <= 224 (B/16: 197 tokens), the streaming ping-pong kernel for
+        // longer sequences (ViT-L/14-336: 577, the 1024 px student: 4097).  CS_ATTN_LEGACY=1 selects the mma.sync kernel
+        // below for A/B measurements; CS_ATTN_FORCE_LONG=1 routes short sequences through the streaming kernel.
         static const bool legacy = env_on("CS_ATTN_LEGACY");
-        // CS_ATTN_FORCE_LONG (with CS_ATTN_LONG_TC): route short sequences through the long-sequence kernel too
-        // (round-2 experiment: its ping-pong schedule against the single-pass kernel at N = 197)
         if (!legacy && !env_on("CS_ATTN_FORCE_LONG")) {
             const int rc = attention_fwd_tc(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
-        // EXPERIMENTAL long-sequence tcgen05 kernel (attention_tc_long.cu): parity-validated, opt-in until timed
-        if (!legacy && env_on("CS_ATTN_LONG_TC")) {
+        if (!legacy) {
             const int rc = attention_fwd_tc_long(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;
         }
@@ -597,8 +596,8 @@ extern "C" int cs_attention_bwd(const void* qkv_bf16, const void* out_bf16, cons
     attn_delta_kernel<<<ceil_div(rows * H, 8), 256, 0, st>>>((const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16,
                                                              rows, N, H, delta_ws);
     CS_LAUNCH_CHECK();
-    // EXPERIMENTAL tcgen05 backward (attention_bwd_tc.cu): staged for round 2, opt-in until validated on hardware
-    if (env_on("CS_ATTN_BWD_TC")) {
+    // tcgen05 backward (attention_bwd_tc.cu); CS_ATTN_LEGACY=1 selects the mma.sync kernels below for A/B measurements
+    if (!env_on("CS_ATTN_LEGACY")) {
         const int rc = attention_bwd_tc(qkv_bf16, d_out_bf16, lse, delta_ws, B, N, H, scale, rope_cos, rope_sin, dqkv_bf16, st);
         if (rc != CS_ERR_UNSUPPORTED) return rc;
     }

@@ -1,9 +1,9 @@
 // tcgen05 / TMA / TMEM GEMM for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T  (bf16 in, f32 accumulate)
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads; with BLOCK_N = 256 the CTAs work in PAIRS (cluster of 2, tcgen05 cta_group::2):
 //   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 64-wide K slabs)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128|256 x BLOCK_N x 16; pair: leader CTA only)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global), two per TMEM lane quarter
 // Pipelines: smem ring full/empty (TMA <-> MMA), double-buffered TMEM accumulator full/empty
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -21,23 +21,31 @@ using namespace cs::tc;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter, splitting the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // + TMA warp + MMA warp
+constexpr int ROPE_STRIDE = 65;                    // [16 freqs][64 grid positions + 1 identity slot]; odd stride: no bank conflicts
 
-template <int BLOCK_N>
+// CG = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
+// CG = 2: a CTA pair (cluster of 2 on one TPC) per 256 x BLOCK_N tile: UMMA M = 256, each CTA owns 128 rows of the
+//         accumulator in its own TMEM and stages only HALF of the B tile (the tensor cores of the pair share it), so the
+//         operand bytes a CTA pulls from L2 per flop drop by a third and 6 instead of 4 stages fit.
+template <int BLOCK_N, int CG = 1>
 struct Cfg {
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int STAGES = (BLOCK_N == 256 && CG == 1) ? 4 : 6;
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int B_ROWS = BLOCK_N / CG;               // rows of W staged by one CTA
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two)
+    static constexpr int HALF_N = BLOCK_N / 2;     // accumulator columns owned by one epilogue warp
     static constexpr int BAR_BYTES = 256;
-    static constexpr int EPI_TILE_BYTES = 32 * 128;          // one swizzled 32-row x 128 B staging tile per warp
-    static constexpr int EPI_BIAS_BYTES = BLOCK_N * 4;       // this tile's bias slice, one private copy per warp
-    static constexpr int EPI_ROWSTAT_BYTES = 256;            // (mean, rstd) of this warp's 32 rows (LN folding)
-    static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + 2 * EPI_BIAS_BYTES + EPI_ROWSTAT_BYTES;  // bias + ln_c1
-    static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-    static constexpr int ROPE_BYTES = 2 * 16 * 64 * 4;       // cos / sin of pos[g] * freq[q]: [2][16 freqs][64 grid positions]
+    static constexpr int EPI_TILE_BYTES = 32 * 64;           // one swizzled 32-row x 64 B staging tile per warp
+    static constexpr int EPI_VEC_BYTES = HALF_N * 4;         // this warp's bias slice / ln_c1 slice
+    static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + 2 * EPI_VEC_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int ROPE_BYTES = 2 * 16 * ROPE_STRIDE * 4;   // cos / sin of pos[g] * freq[q]
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + ROPE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct EpiParams {
@@ -61,43 +69,48 @@ struct EpiParams {
     int ln_parts;
     float ln_inv_dim;
     float ln_eps;
-    float* stats_out;        // SWIGLU: per (row, tile) partial sum / sumsq of the bf16 outputs
+    float* stats_out;        // SWIGLU / EMIT: per (row, tile, column half) partial sum / sumsq of the outputs
+    __nv_bfloat16* out2;     // EMIT: bf16 copy of the f32 output
+    long long ldo2;
     int k_splits;            // split-K factor (RES_RED accumulate into a zeroed output), 1 = off
     int kb_per_split;
 };
 
 enum ResKind { RES_NONE = 0, RES_LOAD = 1, RES_RED = 2 };
 
-// one epilogue warp: 32 accumulator rows of one tile
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t taddr, int mw, int n0, int M, int N,
-                                              uint8_t* st, float* sbias, const float* srope, int lane, bool use_bias) {
+// One epilogue warp: 32 accumulator rows (its TMEM lane quarter) x one column half of one tile.
+//   bf16 outputs: math in the row-per-thread layout of tcgen05.ld.32x32b, 32 output columns (64 B per row) per round
+//   f32 outputs : 16 columns (64 B per row) per round, bias / residual / statistics in the coalesced phase
+// Either way a round goes through this warp's XOR-swizzled 32 x 64 B staging tile so that global accesses are
+// whole 32 B sectors of consecutive rows.
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t taddr, int mw, int n0, int half, int M, int N,
+                                              uint8_t* st, float* sbias, const float* srope, int lane, bool use_bias,
+                                              uint32_t tfull, uint32_t tfull_phase) {
     using C = Cfg<BLOCK_N>;
-    const int crow = lane >> 3;                   // coalesced phase: row within a group of 4
-    const int cchunk = lane & 7;                  // coalesced phase: 16 B chunk of the 128 B row slice
-    // this tile's bias slice -> private smem copy (replaces dependent global loads in the hot loop)
-    if (ep.bias != nullptr && use_bias) {
+    constexpr int HALF_N = C::HALF_N;
+    constexpr bool SWI = (MODE == CS_EPI_SWIGLU);
+    float* sc1 = sbias + HALF_N;
+    // accumulator column of local index j of this warp's slice (SWIGLU: 64 gate columns then the 64 matching up columns)
+    auto acc_col = [&](int j) { return SWI ? ((j < HALF_N / 2) ? half * (HALF_N / 2) + j : BLOCK_N / 2 + half * (HALF_N / 2) + (j - HALF_N / 2))
+                                           : half * HALF_N + j; };
+    // this warp's bias / ln_c1 slices -> private smem (broadcast reads in the hot loops)
 #pragma unroll
-        for (int j = lane * 4; j < BLOCK_N; j += 128) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + j < N) b = *reinterpret_cast<const float4*>(ep.bias + n0 + j);
-            *reinterpret_cast<float4*>(sbias + j) = b;
+    for (int j = lane * 4; j < HALF_N; j += 128) {
+        const int n = n0 + acc_col(j);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), c = b;
+        if (n < N) {
+            if (ep.bias != nullptr && use_bias) b = *reinterpret_cast<const float4*>(ep.bias + n);
+            if constexpr (LNFOLD) c = *reinterpret_cast<const float4*>(ep.ln_c1 + n);
         }
-    } else {
-#pragma unroll
-        for (int j = lane * 4; j < BLOCK_N; j += 128) *reinterpret_cast<float4*>(sbias + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sbias + j) = b;
+        if constexpr (LNFOLD) *reinterpret_cast<float4*>(sc1 + j) = c;
     }
-    float* sc1 = sbias + BLOCK_N;
-    float* srow = sc1 + BLOCK_N;
+    // (mean, rstd) of input row mw + lane from its partial sums
+    float rs = 1.f, rm = 0.f;                     // rstd, rstd * mean
     if constexpr (LNFOLD) {
-#pragma unroll
-        for (int j = lane * 4; j < BLOCK_N; j += 128) {
-            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + j < N) c = *reinterpret_cast<const float4*>(ep.ln_c1 + n0 + j);
-            *reinterpret_cast<float4*>(sc1 + j) = c;
-        }
-        // (mean, rstd) of input row mw + lane from its partial sums
-        float mu = 0.f, rs = 0.f;
+        float mu = 0.f;
+        rs = 0.f;
         if (mw + lane < M) {
             const float* ps = ep.ln_stats + (long long)(mw + lane) * ep.ln_parts * 2;
             float s1 = 0.f, s2 = 0.f;
@@ -110,113 +123,132 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
             const float var = fmaxf(s2 * ep.ln_inv_dim - mu * mu, 0.f);
             rs = rsqrtf(var + ep.ln_eps);
         }
-        srow[lane * 2] = mu;
-        srow[lane * 2 + 1] = rs;
+        rm = rs * mu;
     }
     __syncwarp();
+    const int swz = (lane >> 1) & 3;                     // row-per-thread phase: 16 B chunk j of row `lane` lives at j ^ swz
+    const int crow = lane >> 2;                          // coalesced phase: row within a group of 8
+    const int cch = lane & 3;                            // coalesced phase: 16 B chunk of the 64 B row slice
+    // Everything above (bias / ln_c1 slices, row statistics) and the first residual reads below do not depend on the
+    // accumulator: they are issued BEFORE waiting for the MMAs of this tile, so their latency hides under the mainloop.
+    auto wait_accumulator = [&]() {
+        mbar_wait(tfull, tfull_phase);
+        tc_fence_after();
+    };
+    if (ep.dbg & 8) {                                    // ablation: mainloop + handshakes only
+        wait_accumulator();
+        return;
+    }
 
     if constexpr (OUT_BF16) {
-        // ---------------- bf16 outputs: math in registers (row per thread), packed staging --------
+        wait_accumulator();
         const int m = mw + lane;
-        int gi = 0, gj = 0;
-        bool rot = false;
+        int gi = 64, gj = 64;                            // slot 64 of the rotary table = identity (CLS rows)
         if constexpr (MODE == CS_EPI_QKV_ROPE) {
             const int tok = m % ep.tokens;
-            rot = tok > 0;
-            const int p = tok > 0 ? tok - 1 : 0;
-            gi = p / ep.rope_grid;
-            gj = p % ep.rope_grid;
+            if (tok > 0) {
+                gi = (tok - 1) / ep.rope_grid;
+                gj = (tok - 1) % ep.rope_grid;
+            }
         }
-        constexpr int OUT_COLS = (MODE == CS_EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N;
-        const int out_n0 = (MODE == CS_EPI_SWIGLU) ? (n0 >> 1) : n0;
-        const int out_N = (MODE == CS_EPI_SWIGLU) ? (N >> 1) : N;
-        float st1 = 0.f, st2 = 0.f;                          // SWIGLU stats_out: row sum / sum of squares of the stored values
+        constexpr int OUT_HALF = SWI ? HALF_N / 2 : HALF_N;        // output columns of this warp
+        const int out_n0 = (SWI ? (n0 >> 1) : n0) + half * OUT_HALF;
+        const int out_N = SWI ? (N >> 1) : N;
+        float st1 = 0.f, st2 = 0.f;                      // SWIGLU stats_out: row sum / sum of squares of the f32 values
 #pragma unroll 1
-        for (int gc = 0; gc < OUT_COLS; gc += 64) {          // 64 bf16 output columns = 128 B per row
-            if (out_n0 + gc >= out_N) break;
+        for (int r = 0; r < OUT_HALF; r += 32) {
+            if (out_n0 + r >= out_N) break;
+            float v[32];
+            if constexpr (SWI) {
+                uint32_t rg[32], ru[32];
+                tmem_ld32(taddr + half * OUT_HALF + r, rg);
+                tmem_ld32(taddr + BLOCK_N / 2 + half * OUT_HALF + r, ru);
+                tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int c = gc + half * 32;                // output column offset inside the tile
-                float v[32];
-                if constexpr (MODE == CS_EPI_SWIGLU) {
-                    uint32_t rg[32], ru[32];
-                    tmem_ld32(taddr + c, rg);
-                    tmem_ld32(taddr + 128 + c, ru);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float g = __uint_as_float(rg[j]) * ep.alpha + sbias[c + j];
-                        const float u = __uint_as_float(ru[j]) * ep.alpha + sbias[128 + c + j];
-                        v[j] = __fdividef(g, 1.0f + __expf(-g)) * u;
+                for (int j = 0; j < 32; ++j) {
+                    float g, u;
+                    if constexpr (LNFOLD) {
+                        g = fmaf(rs, __uint_as_float(rg[j]), fmaf(-rm, sc1[r + j], sbias[r + j]));
+                        u = fmaf(rs, __uint_as_float(ru[j]), fmaf(-rm, sc1[OUT_HALF + r + j], sbias[OUT_HALF + r + j]));
+                    } else {
+                        g = fmaf(__uint_as_float(rg[j]), ep.alpha, sbias[r + j]);
+                        u = fmaf(__uint_as_float(ru[j]), ep.alpha, sbias[OUT_HALF + r + j]);
                     }
+                    v[j] = __fdividef(g, 1.0f + __expf(-g)) * u;
+                    st1 += v[j];
+                    st2 = fmaf(v[j], v[j], st2);
+                }
+            } else {
+                uint32_t a[32];
+                if (ep.dbg & 4) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = (uint32_t)(r + j + lane);
                 } else {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c, r);
+                    tmem_ld32(taddr + half * HALF_N + r, a);
                     tmem_ld_wait();
+                }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha + sbias[c + j];
-                    if constexpr (MODE == CS_EPI_QKV_ROPE) {
-                        const int n = n0 + c;
-                        if (n < ep.rope_cols && rot) {
-                            // head-dim offset 0..31 rotates by the token's grid ROW, 32..63 by its COLUMN
-                            const int g = (n & 32) ? gj : gi;
+                for (int j = 0; j < 32; ++j) {
+                    if constexpr (LNFOLD) v[j] = fmaf(rs, __uint_as_float(a[j]), fmaf(-rm, sc1[r + j], sbias[r + j]));
+                    else v[j] = fmaf(__uint_as_float(a[j]), ep.alpha, sbias[r + j]);
+                }
+                if constexpr (MODE == CS_EPI_QKV_ROPE) {
+                    const int n = n0 + half * HALF_N + r;
+                    if (n < ep.rope_cols) {
+                        // head-dim offset 0..31 rotates by the token's grid ROW, 32..63 by its COLUMN
+                        const float* tc = srope + ((n & 32) ? gj : gi);
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                const float cs_ = srope[q * 64 + g], sn = srope[1024 + q * 64 + g];
-                                const float x0 = v[2 * q], x1 = v[2 * q + 1];
-                                v[2 * q] = x0 * cs_ - x1 * sn;
-                                v[2 * q + 1] = x1 * cs_ + x0 * sn;
-                            }
+                        for (int q = 0; q < 16; ++q) {
+                            const float cs_ = tc[q * ROPE_STRIDE], sn = tc[16 * ROPE_STRIDE + q * ROPE_STRIDE];
+                            const float x0 = v[2 * q], x1 = v[2 * q + 1];
+                            v[2 * q] = fmaf(x0, cs_, -x1 * sn);
+                            v[2 * q + 1] = fmaf(x1, cs_, x0 * sn);
                         }
                     }
                 }
+            }
+            if (ep.dbg & 2) {            // ablation: math only (keep the values alive without touching smem / global)
+                float acc = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 pk;
-                    pk.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-                    pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                    pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                    pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                    const int chunk = half * 4 + j;
-                    *reinterpret_cast<uint4*>(st + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
-                    if constexpr (MODE == CS_EPI_SWIGLU) {
-                        // row statistics for the folded ffn_ln (from the f32 values: the bf16 rounding of
-                        // the stored h is zero-mean noise ~2^-9/sqrt(n) on the mean, negligible)
+                for (int j = 0; j < 32; ++j) acc += v[j];
+                if (acc == 1.2345e-30f) *reinterpret_cast<float*>(ep.out) = acc;
+                continue;
+            }
 #pragma unroll
-                        for (int z = 0; z < 8; ++z) {
-                            st1 += v[8 * j + z];
-                            st2 += v[8 * j + z] * v[8 * j + z];
-                        }
-                    }
-                }
+            for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                pk.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+                pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(st + lane * 64 + ((j ^ swz) << 4)) = pk;
             }
             __syncwarp();
-            const int ocol = out_n0 + gc + cchunk * 8;
-            uint4 val[8];
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(ep.out) + out_n0 + r + cch * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = i * 4 + crow;
-                val[i] = *reinterpret_cast<const uint4*>(st + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int mm = mw + i * 4 + crow;
-                if (mm < M && ocol < out_N)
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)mm * ep.ldo + ocol) = val[i];
+            for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + crow;
+                const uint4 val = *reinterpret_cast<const uint4*>(st + rr * 64 + ((cch ^ ((rr >> 1) & 3)) << 4));
+                if (mw + rr < M && !(ep.dbg & 1))      // ablation bit 0: no global stores
+                    *reinterpret_cast<uint4*>(obase + (long long)(mw + rr) * ep.ldo) = val;
             }
             __syncwarp();
         }
-        if constexpr (MODE == CS_EPI_SWIGLU) {
+        if constexpr (SWI) {
             if (ep.stats_out != nullptr && m < M)
-                *reinterpret_cast<float2*>(ep.stats_out + ((long long)m * (N / BLOCK_N) + n0 / BLOCK_N) * 2) = make_float2(st1, st2);
+                *reinterpret_cast<float2*>(ep.stats_out + (((long long)m * (N / BLOCK_N) + n0 / BLOCK_N) * 2 + half) * 2) =
+                    make_float2(st1, st2);
         }
     } else {
-        // ---------------- f32 outputs: raw staging, math in the coalesced phase ----------------
-        long long orow[8];
-        int prow[8];
+        // ---------------- f32 outputs ----------------
+        constexpr int ROUNDS = HALF_N / 16;
+        constexpr bool HAS_EXTRA = (RES == RES_LOAD) || (MODE == CS_EPI_TOKENS);
+        constexpr int PF = HAS_EXTRA ? 4 : 1;            // rounds of residual / pos_embed reads kept in flight per thread
+        long long orow[4];
+        int prow[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int mm = mw + i * 4 + crow;
+        for (int i = 0; i < 4; ++i) {
+            const int mm = mw + i * 8 + crow;
             orow[i] = mm;
             prow[i] = 0;
             if constexpr (MODE == CS_EPI_TOKENS) {
@@ -225,72 +257,107 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
             }
             if (mm >= M) orow[i] = -1;
         }
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {              // 32 f32 output columns = 128 B per row
-            const int n = n0 + c;
-            if (n >= N) break;
-            const int nc = n + cchunk * 4;
-            const bool col_ok = nc < N;
-            // residual / pos_embed reads do not depend on the accumulator: issue them first
-            float4 extra[8];
+        const int nbase = n0 + half * HALF_N + cch * 4;  // this lane's first output column
+        float4 extra[PF][4];
+        auto fetch_extra = [&](int rd, float4 (&dst)[4]) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                extra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (orow[i] >= 0 && col_ok) {
-                    if constexpr (RES == RES_LOAD) extra[i] = *reinterpret_cast<const float4*>(ep.residual + orow[i] * ep.ldr + nc);
-                    if constexpr (MODE == CS_EPI_TOKENS) extra[i] = *reinterpret_cast<const float4*>(ep.pos_embed + (long long)prow[i] * N + nc);
+            for (int i = 0; i < 4; ++i) {
+                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (orow[i] >= 0 && nbase + rd * 16 < N) {
+                    if constexpr (RES == RES_LOAD) dst[i] = *reinterpret_cast<const float4*>(ep.residual + orow[i] * ep.ldr + nbase + rd * 16);
+                    if constexpr (MODE == CS_EPI_TOKENS) dst[i] = *reinterpret_cast<const float4*>(ep.pos_embed + (long long)prow[i] * N + nbase + rd * 16);
                 }
             }
-            {
-                uint32_t r[32];
-                tmem_ld32(taddr + c, r);
+        };
+        if constexpr (HAS_EXTRA) {
+#pragma unroll
+            for (int p = 0; p < PF && p < ROUNDS; ++p) fetch_extra(p, extra[p]);
+        }
+        wait_accumulator();
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};      // EMIT: statistics of this lane's 4 rows
+#pragma unroll
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+            const int r = rd * 16;
+            const int nc = nbase + r;
+            const bool col_ok = n0 + half * HALF_N + r < N;          // warp-uniform (N % 32 == 0)
+            float4 ex[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ex[i] = HAS_EXTRA ? extra[rd % PF][i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (HAS_EXTRA) {
+                if (rd + PF < ROUNDS) fetch_extra(rd + PF, extra[rd % PF]);
+            }
+            if (col_ok) {
+                uint32_t a[16];
+                tmem_ld16(taddr + half * HALF_N + r, a);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 f = make_float4(__uint_as_float(r[4 * j]) * ep.alpha, __uint_as_float(r[4 * j + 1]) * ep.alpha,
-                                                 __uint_as_float(r[4 * j + 2]) * ep.alpha, __uint_as_float(r[4 * j + 3]) * ep.alpha);
-                    *reinterpret_cast<float4*>(st + lane * 128 + ((j ^ (lane & 7)) << 4)) = f;
+                for (int j = 0; j < 4; ++j) {
+                    float4 f;
+                    if constexpr (LNFOLD) {
+                        f.x = fmaf(rs, __uint_as_float(a[4 * j]), -rm * sc1[r + 4 * j]);
+                        f.y = fmaf(rs, __uint_as_float(a[4 * j + 1]), -rm * sc1[r + 4 * j + 1]);
+                        f.z = fmaf(rs, __uint_as_float(a[4 * j + 2]), -rm * sc1[r + 4 * j + 2]);
+                        f.w = fmaf(rs, __uint_as_float(a[4 * j + 3]), -rm * sc1[r + 4 * j + 3]);
+                    } else {
+                        f = make_float4(__uint_as_float(a[4 * j]) * ep.alpha, __uint_as_float(a[4 * j + 1]) * ep.alpha,
+                                        __uint_as_float(a[4 * j + 2]) * ep.alpha, __uint_as_float(a[4 * j + 3]) * ep.alpha);
+                    }
+                    *reinterpret_cast<float4*>(st + lane * 64 + ((j ^ swz) << 4)) = f;
                 }
             }
             __syncwarp();
-            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + cchunk * 4);
-            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (LNFOLD) c4 = *reinterpret_cast<const float4*>(sc1 + c + cchunk * 4);
+            if (col_ok) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sbias + r + cch * 4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = i * 4 + crow;
-                float4 f = *reinterpret_cast<const float4*>(st + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
-                if constexpr (LNFOLD) {
-                    const float2 ms = *reinterpret_cast<const float2*>(srow + rr * 2);      // (mean, rstd) of the input row
-                    f.x = ms.y * (f.x - ms.x * c4.x);
-                    f.y = ms.y * (f.y - ms.x * c4.y);
-                    f.z = ms.y * (f.z - ms.x * c4.z);
-                    f.w = ms.y * (f.w - ms.x * c4.w);
-                }
-                f.x += b4.x + extra[i].x;
-                f.y += b4.y + extra[i].y;
-                f.z += b4.z + extra[i].z;
-                f.w += b4.w + extra[i].w;
-                if (orow[i] >= 0 && col_ok) {
-                    float* dst = reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + nc;
-                    if constexpr (RES == RES_RED) {
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w)
-                                     : "memory");
-                    } else {
-                        *reinterpret_cast<float4*>(dst) = f;
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = i * 8 + crow;
+                    float4 f = *reinterpret_cast<const float4*>(st + rr * 64 + ((cch ^ ((rr >> 1) & 3)) << 4));
+                    f.x += b4.x + ex[i].x;
+                    f.y += b4.y + ex[i].y;
+                    f.z += b4.z + ex[i].z;
+                    f.w += b4.w + ex[i].w;
+                    if (orow[i] >= 0 && !(ep.dbg & 1)) {
+                        float* dst = reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + nc;
+                        if constexpr (RES == RES_RED) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w)
+                                         : "memory");
+                        } else {
+                            *reinterpret_cast<float4*>(dst) = f;
+                        }
+                        if constexpr (EMIT) {
+                            uint2 pk;
+                            pk.x = pack_bf16(f.x, f.y);
+                            pk.y = pack_bf16(f.z, f.w);
+                            *reinterpret_cast<uint2*>(ep.out2 + orow[i] * ep.ldo2 + nc) = pk;
+                            s1[i] += (f.x + f.y) + (f.z + f.w);
+                            s2[i] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, s2[i]))));
+                        }
                     }
                 }
             }
             __syncwarp();
         }
+        if constexpr (EMIT) {
+            // the 4 lanes of a row hold its partial sums: combine, lane cch == 0 writes (row, tile, half)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 1);
+                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 1);
+                s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 2);
+                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 2);
+                if (cch == 0 && orow[i] >= 0 && ep.stats_out != nullptr)
+                    *reinterpret_cast<float2*>(ep.stats_out + ((orow[i] * ((N + BLOCK_N - 1) / BLOCK_N) + n0 / BLOCK_N) * 2 + half) * 2) =
+                        make_float2(s1[i], s2[i]);
+            }
+        }
     }
 }
 
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             int M, int N, int K, const EpiParams ep) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
@@ -305,13 +372,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    static_assert(8 * (2 * C::STAGES + 5) <= C::BAR_BYTES, "barrier area");
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + 8 * (2 * C::STAGES + 4));
     float* srope = reinterpret_cast<float*>(smem + ROPE_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    // work unit: one (CG*128) x BLOCK_N tile per CTA group; `rank` = this CTA's half of it
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int group = (int)blockIdx.x / CG, num_groups = (int)gridDim.x / CG;
+    const int num_m_tiles = (M + CG * BLOCK_M - 1) / (CG * BLOCK_M);
     const int num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_mn = num_m_tiles * num_n_tiles;
     const int num_tiles = num_mn * ep.k_splits;          // split-K: tile t -> (mn = t % num_mn, split = t / num_mn)
@@ -326,45 +397,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4 * 32);
+            mbar_init(tempty_bar(a), CG * EPI_WARPS * 32);     // CG = 2: the leader's barrier collects both CTAs' epilogues
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if constexpr (MODE == CS_EPI_QKV_ROPE) {
         // rotary table of this launch: angle(g, q) = pos[g] * freq[q] (f32 product as in rope.py:129), accurate
-        // sincosf once per CTA; layout [q][g] so that lanes with different grid positions hit different banks
-        for (int i = threadIdx.x; i < 16 * 64; i += NUM_THREADS) {
-            const int q = i >> 6, g = i & 63;
+        // sincosf once per CTA; layout [q][g], g = 64 is the identity rotation used by the CLS rows
+        for (int i = threadIdx.x; i < 16 * ROPE_STRIDE; i += NUM_THREADS) {
+            const int q = i / ROPE_STRIDE, g = i % ROPE_STRIDE;
             float sn = 0.f, cs_ = 1.f;
             if (g < ep.rope_grid) sincosf(ep.rope_pos[g] * ep.rope_freq[q], &sn, &cs_);
             srope[i] = cs_;
-            srope[1024 + i] = sn;
+            srope[16 * ROPE_STRIDE + i] = sn;
         }
     }
-    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 1) {
+        if constexpr (CG == 2) tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);       // one warp of EACH CTA of the pair
+        else tmem_alloc(tmem_slot, C::TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
+        // CG = 2: both CTAs load their own A rows and their half of the B rows into their own shared memory; all bytes
+        // are counted on the LEADER's full barrier (the only MMA issuer), which expects both CTAs' stage bytes.
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = group; tile < num_tiles; tile += num_groups) {
                 const int mn = tile % num_mn, sp = tile / num_mn;
-                const int m0 = (mn / num_n_tiles) * BLOCK_M;
-                const int n0 = (mn % num_n_tiles) * BLOCK_N;
+                const int m0 = (mn / num_n_tiles) * (CG * BLOCK_M) + (int)rank * BLOCK_M;
+                const int n0 = (mn % num_n_tiles) * BLOCK_N + (int)rank * C::B_ROWS * (CG - 1);
                 const int kb0 = sp * ep.kb_per_split;
                 const int kb1 = min(num_kb_total, kb0 + ep.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + C::A_BYTES;
-                    mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                    tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m0);
-                    tma_load_2d(sb, &map_b, full_bar(stage), kb * BLOCK_K, n0);
+                    if constexpr (CG == 2) {
+                        const uint32_t fb = map_to_cta(full_bar(stage), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                        tma_load_2d_cg2(sa, &map_a, fb, kb * BLOCK_K, m0);
+                        tma_load_2d_cg2(sb, &map_b, fb, kb * BLOCK_K, n0);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                        tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m0);
+                        tma_load_2d(sb, &map_b, full_bar(stage), kb * BLOCK_K, n0);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -373,13 +457,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
         }
     } else if (warp == 1) {
-        // ------------------------------ MMA issuer --------------------------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+        // ------------------------------ MMA issuer (CG = 2: leader CTA only) --------
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(CG * BLOCK_M, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue drained this accumulator
@@ -397,11 +481,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr>>4)
-                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                  (kb > kb0 || k > 0) ? 1u : 0u);
+                        if constexpr (CG == 2)
+                            umma_bf16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(stage));             // frees the smem slot when MMAs retire
-                    if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+                    if constexpr (CG == 2) {
+                        umma_commit_cg2(empty_bar(stage), 3);      // frees the slot in BOTH CTAs when the MMAs retire
+                        if (kb == kb1 - 1) umma_commit_cg2(tfull_bar(acc), 3);
+                    } else {
+                        umma_commit(empty_bar(stage));             // frees the smem slot when MMAs retire
+                        if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -411,69 +502,119 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
     } else {
         // ------------------------------ epilogue -----------------------------------
-        // Each warp owns 32 accumulator rows (its TMEM lane quarter); see epilogue_tile().
+        // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         uint8_t* st = smem + EPI_OFF + (warp - 2) * C::EPI_WARP_BYTES;
         float* sbias = reinterpret_cast<float*>(st + C::EPI_TILE_BYTES);
+        const uint32_t tempty_leader0 = (CG == 2) ? map_to_cta(tempty_bar(0), 0) : 0u;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
             const int mn = tile % num_mn;
-            const int m0 = (mn / num_n_tiles) * BLOCK_M;
+            const int m0 = (mn / num_n_tiles) * (CG * BLOCK_M) + (int)rank * BLOCK_M;
             const int n0 = (mn % num_n_tiles) * BLOCK_N;
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            if (!(ep.dbg & 8))
-                epilogue_tile<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD>(ep, taddr, m0 + quarter * 32, n0, M, N, st, sbias, srope, lane,
-                                                                    tile < num_mn);
+            epilogue_tile<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT>(ep, taddr, m0 + quarter * 32, n0, half, M, N, st, sbias,
+                                                                      srope, lane, tile < num_mn, tfull_bar(acc), acc_phase);
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);
+            else mbar_arrive(tempty_bar(acc));
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CG == 2) cluster_sync_all();      // nobody leaves while the peer may still signal into its shared memory
+    if (warp == 1) {
+        if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+        else tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
 }
 
 // ----------------------------------------------------------------------------------------
 // Host side
 // ----------------------------------------------------------------------------------------
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD = false>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
-                  cudaStream_t stream) {
-    using C = Cfg<BLOCK_N>;
+// BLOCK_N = 256 runs on CTA pairs (cta_group::2) unless CS_GEMM_1CTA=1 (A/B measurements against the single-CTA kernel)
+static bool use_cta_pairs() {
+    static const int v = [] {
+        const char* e = getenv("CS_GEMM_1CTA");
+        return (e != nullptr && e[0] != '\0' && e[0] != '0') ? 0 : 1;
+    }();
+    return v != 0;
+}
+
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG>
+static int launch_cg(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
+                     cudaStream_t stream) {
+    using C = Cfg<BLOCK_N, CG>;
+    auto kern = gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, CG>;
     static bool configured = false;
     if (!configured) {
-        CS_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
-    CS_LAUNCH_CHECK();
+    const long long tiles = (long long)ceil_div(M, CG * BLOCK_M) * ceil_div(N, BLOCK_N) * ep.k_splits;   // split-K tiles included
+    const int max_groups = num_sms() / CG;
+    const int groups = tiles < max_groups ? (int)tiles : max_groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * CG));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
     return CS_OK;
 }
 
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD = false, bool EMIT = false>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb2, const CUtensorMap& mb1, int M, int N, int K, const EpiParams& ep,
+                  cudaStream_t stream) {
+    if constexpr (BLOCK_N == 256) {
+        if (use_cta_pairs()) return launch_cg<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, 2>(ma, mb2, M, N, K, ep, stream);
+    }
+    return launch_cg<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, 1>(ma, mb1, M, N, K, ep, stream);
+}
+
+// mb2: B map with the box of a CTA pair member (BLOCK_N / 2 rows); mb: box of BLOCK_N rows (single-CTA kernel)
 template <int BLOCK_N>
-static int dispatch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep, int res,
-                    cudaStream_t st) {
+static int dispatch(const CUtensorMap& ma, const CUtensorMap& mb2, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
+                    int res, cudaStream_t st) {
+    const bool fold = ep.ln_stats != nullptr, emit = ep.out2 != nullptr;
     switch (ep.mode) {
         case CS_EPI_STORE:
-            if (ep.out_bf16) return launch<BLOCK_N, CS_EPI_STORE, true, RES_NONE>(ma, mb, M, N, K, ep, st);
-            if (res == RES_RED && ep.ln_stats != nullptr) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED, true>(ma, mb, M, N, K, ep, st);
-            if (res == RES_RED) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED>(ma, mb, M, N, K, ep, st);
-            if (res == RES_LOAD) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD>(ma, mb, M, N, K, ep, st);
-            return launch<BLOCK_N, CS_EPI_STORE, false, RES_NONE>(ma, mb, M, N, K, ep, st);
+            if (ep.out_bf16) {
+                if (fold) return launch<BLOCK_N, CS_EPI_STORE, true, RES_NONE, true>(ma, mb2, mb, M, N, K, ep, st);
+                return launch<BLOCK_N, CS_EPI_STORE, true, RES_NONE>(ma, mb2, mb, M, N, K, ep, st);
+            }
+            if (emit) {         // new f32 residual stream + its bf16 copy + row statistics
+                if (res == RES_LOAD && fold) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD, true, true>(ma, mb2, mb, M, N, K, ep, st);
+                if (res == RES_LOAD) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD, false, true>(ma, mb2, mb, M, N, K, ep, st);
+                break;
+            }
+            if (res == RES_RED && fold) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED, true>(ma, mb2, mb, M, N, K, ep, st);
+            if (res == RES_LOAD && fold) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD, true>(ma, mb2, mb, M, N, K, ep, st);
+            if (fold) break;
+            if (res == RES_RED) return launch<BLOCK_N, CS_EPI_STORE, false, RES_RED>(ma, mb2, mb, M, N, K, ep, st);
+            if (res == RES_LOAD) return launch<BLOCK_N, CS_EPI_STORE, false, RES_LOAD>(ma, mb2, mb, M, N, K, ep, st);
+            return launch<BLOCK_N, CS_EPI_STORE, false, RES_NONE>(ma, mb2, mb, M, N, K, ep, st);
         case CS_EPI_QKV_ROPE:
-            return launch<BLOCK_N, CS_EPI_QKV_ROPE, true, RES_NONE>(ma, mb, M, N, K, ep, st);
+            if (fold) return launch<BLOCK_N, CS_EPI_QKV_ROPE, true, RES_NONE, true>(ma, mb2, mb, M, N, K, ep, st);
+            return launch<BLOCK_N, CS_EPI_QKV_ROPE, true, RES_NONE>(ma, mb2, mb, M, N, K, ep, st);
         case CS_EPI_TOKENS:
-            return launch<BLOCK_N, CS_EPI_TOKENS, false, RES_NONE>(ma, mb, M, N, K, ep, st);
+            return launch<BLOCK_N, CS_EPI_TOKENS, false, RES_NONE>(ma, mb2, mb, M, N, K, ep, st);
         case CS_EPI_SWIGLU:
-            if constexpr (BLOCK_N == 256) return launch<256, CS_EPI_SWIGLU, true, RES_NONE>(ma, mb, M, N, K, ep, st);
+            if constexpr (BLOCK_N == 256) {
+                if (fold) return launch<256, CS_EPI_SWIGLU, true, RES_NONE, true>(ma, mb2, mb, M, N, K, ep, st);
+                return launch<256, CS_EPI_SWIGLU, true, RES_NONE>(ma, mb2, mb, M, N, K, ep, st);
+            }
     }
     set_error("cs_gemm_bf16: unsupported epilogue combination");
     return CS_ERR_UNSUPPORTED;
@@ -522,6 +663,8 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     ep.ln_inv_dim = e->ln_dim > 0 ? 1.0f / (float)e->ln_dim : 0.f;
     ep.ln_eps = e->ln_eps;
     ep.stats_out = e->stats_out;
+    ep.out2 = reinterpret_cast<__nv_bfloat16*>(e->out2_bf16);
+    ep.ldo2 = e->ldo2;
     ep.k_splits = 1;
     ep.kb_per_split = ceil_div(K, BLOCK_K);
 
@@ -539,36 +682,48 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
         CS_CHECK_ARG(e->pos_embed && e->tokens > 1 && e->out_dtype == CS_F32 && ((uintptr_t)e->pos_embed % 16 == 0),
                      "cs_gemm_bf16: TOKENS needs pos_embed, tokens, f32 out");
 
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mb2;
     int rc = make_map_bf16_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M);
     if (rc) return rc;
     rc = make_map_bf16_2d(&mb, W, N, K, ldw, BLOCK_K, use256 ? 256 : 128);
     if (rc) return rc;
+    mb2 = mb;
+    if (use256 && use_cta_pairs()) {
+        rc = make_map_bf16_2d(&mb2, W, N, K, ldw, BLOCK_K, 128);       // each CTA of a pair stages 128 of the tile's 256 W rows
+        if (rc) return rc;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int res = RES_NONE;
     if (e->residual) {
         CS_CHECK_ARG(e->out_dtype == CS_F32 && e->mode == CS_EPI_STORE, "cs_gemm_bf16: residual needs f32 STORE output");
-        res = (e->residual == e->out && e->ldr == e->ldo) ? RES_RED : RES_LOAD;
+        res = (e->residual == e->out && e->ldr == e->ldo && e->out2_bf16 == nullptr) ? RES_RED : RES_LOAD;
     }
     if (e->ln_stats)
-        CS_CHECK_ARG(res == RES_RED && e->ln_c1 && e->ln_parts > 0 && e->ln_parts % 2 == 0 && e->ln_dim > 0 &&
-                         ((uintptr_t)e->ln_stats % 16 == 0) && ((uintptr_t)e->ln_c1 % 16 == 0),
-                     "cs_gemm_bf16: LN folding needs the in-place f32 residual epilogue, ln_c1, even ln_parts, ln_dim");
-    if (e->stats_out) CS_CHECK_ARG(e->mode == CS_EPI_SWIGLU, "cs_gemm_bf16: stats_out is a SWIGLU output");
+        CS_CHECK_ARG(e->ln_c1 && e->ln_parts > 0 && e->ln_parts % 2 == 0 && e->ln_dim > 0 && e->alpha == 1.0f &&
+                         e->mode != CS_EPI_TOKENS && ((uintptr_t)e->ln_stats % 16 == 0) && ((uintptr_t)e->ln_c1 % 16 == 0),
+                     "cs_gemm_bf16: LN folding needs ln_c1, even ln_parts, ln_dim, alpha == 1 (any mode but TOKENS)");
+    if (e->out2_bf16)
+        CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual && ((uintptr_t)e->out2_bf16 % 8 == 0) &&
+                         e->ldo2 % 4 == 0,
+                     "cs_gemm_bf16: out2_bf16 (bf16 copy + row statistics of the new residual stream) needs the f32 STORE "
+                     "epilogue with a residual");
+    if (e->stats_out) CS_CHECK_ARG(e->mode == CS_EPI_SWIGLU || e->out2_bf16, "cs_gemm_bf16: stats_out is a SWIGLU / out2_bf16 output");
     if (e->reserved2 != 0) {
         // split-K (reserved2 = requested splits, -1 = choose): partial products are accumulated with
         // red.add into `out`, which the caller must have zeroed.  f32 STORE without residual only.
         CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual == nullptr && e->ln_stats == nullptr,
                      "cs_gemm_bf16: split-K needs a plain f32 STORE epilogue");
         const int num_kb = ceil_div(K, BLOCK_K);
-        const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, use256 ? 256 : 128);
+        const int cg = (use256 && use_cta_pairs()) ? 2 : 1;            // work units and CTA groups of the kernel that will run
+        const int tiles = ceil_div(M, cg * BLOCK_M) * ceil_div(N, use256 ? 256 : 128);
+        const int groups = num_sms() / cg;
         int best = 1;
         if (e->reserved2 > 0) {
             best = e->reserved2;
         } else {
             long long best_cost = -1;
-            for (int sp = 1; sp <= 8 && sp <= num_kb; ++sp) {
-                const long long waves = ceil_div((long long)tiles * sp, num_sms());
+            for (int sp = 1; sp <= 16 && sp <= num_kb; ++sp) {
+                const long long waves = ceil_div((long long)tiles * sp, groups);
                 const long long cost = waves * (ceil_div(num_kb, sp) + 8);     // +8 k-blocks ~ per-tile epilogue/fill cost
                 if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
             }
@@ -581,5 +736,5 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
             res = RES_RED;
         }
     }
-    return use256 ? dispatch<256>(ma, mb, (int)M, N, K, ep, res, st) : dispatch<128>(ma, mb, (int)M, N, K, ep, res, st);
+    return use256 ? dispatch<256>(ma, mb2, mb, (int)M, N, K, ep, res, st) : dispatch<128>(ma, mb2, mb, (int)M, N, K, ep, res, st);
 }

@@ -279,7 +279,7 @@ using namespace cs;
 using namespace cs::rowops;
 
 extern "C" const char* cs_last_error(void) { return cs::g_err; }
-extern "C" int cs_abi_version(void) { return 2; }
+extern "C" int cs_abi_version(void) { return 3; }
 
 extern "C" int cs_device_info(int* sm_out, int* num_sms_out, int64_t* hbm_bytes_out) {
     int dev = 0;
@@ -344,6 +344,49 @@ extern "C" int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, 
         layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, smem, st>>>(
             (const __nv_bfloat16*)x, ldx, M, D, row_div, row_mul, row_off, gamma, beta, eps, (__nv_bfloat16*)y_bf16, ldy, mean, rstd);
     }
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+// f32 rows -> bf16 copy + (sum, sum of squares) partials in the layout the LayerNorm-folded GEMM epilogues read
+// (cs_gemm_epilogue_t.ln_stats): the whole-row statistics go to part 0, the remaining parts are zero.
+namespace cs {
+namespace rowops {
+__global__ void __launch_bounds__(256)
+row_stats_cast_kernel(const float* __restrict__ x, long long ldx, long long M, int D, __nv_bfloat16* __restrict__ xb,
+                      long long ldb, float* __restrict__ stats, int parts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * 8 + warp;
+    if (m >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + m * ldx);
+    uint2* br = reinterpret_cast<uint2*>(xb + m * ldb);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < D / 4; i += 32) {
+        const float4 v = xr[i];
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+        uint2 pk;
+        pk.x = pack_bf16(v.x, v.y);
+        pk.y = pack_bf16(v.z, v.w);
+        br[i] = pk;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    float2* sr = reinterpret_cast<float2*>(stats + m * parts * 2);
+    for (int q = lane; q < parts; q += 32) sr[q] = q == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+}  // namespace rowops
+}  // namespace cs
+
+extern "C" int cs_row_stats_cast(const float* x, int64_t ldx, int64_t M, int D, void* xb_bf16, int64_t ldb,
+                                 float* stats, int parts, void* stream) {
+    using namespace cs;
+    CS_CHECK_ARG(x && xb_bf16 && stats && M > 0 && D > 0 && D % 4 == 0 && ldx % 4 == 0 && ldb % 4 == 0 && parts > 0,
+                 "cs_row_stats_cast: bad arguments (D, ldx, ldb multiples of 4; parts > 0)");
+    CS_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)xb_bf16 % 8 == 0) && ((uintptr_t)stats % 8 == 0),
+                 "cs_row_stats_cast: alignment");
+    rowops::row_stats_cast_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, M, D, (__nv_bfloat16*)xb_bf16, ldb, stats, parts);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

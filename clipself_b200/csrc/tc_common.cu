@@ -1,6 +1,9 @@
 // Host-side tensor-map construction shared by the TMA kernels.
 #include "tc_common.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace cs {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -20,9 +23,55 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2D bf16 row-major [rows, cols] with leading dimension ld; box = [box_rows, box_cols], 128B swizzle.
+// Descriptor cache: a tensor map depends only on (address, geometry, box), so steady-state steps (same workspace
+// buffers every step) never call into the driver.  Bounded; dropped wholesale when full.
+namespace {
+struct MapKey {
+    const void* ptr;
+    int64_t rows, cols, ld;
+    int box_cols, box_rows;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)k.rows * 0xC2B2AE3D27D4EB4Full) ^ ((uint64_t)k.cols << 17) ^ ((uint64_t)k.ld << 41) ^
+             ((uint64_t)k.box_cols << 7) ^ ((uint64_t)k.box_rows << 29);
+        return (size_t)(h ^ (h >> 31));
+    }
+};
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+long long g_map_encodes = 0;
+}  // namespace
+
+long long tensor_map_encode_count() { return g_map_encodes; }
+
+static int encode_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                              int box_rows);
+
 int make_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                      int box_rows) {
+    const MapKey key{ptr, rows, cols, ld, box_cols, box_rows};
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+        *map = it->second;
+        return CS_OK;
+    }
+    const int rc = encode_map_bf16_2d(map, ptr, rows, cols, ld, box_cols, box_rows);
+    if (rc != CS_OK) return rc;
+    if (g_map_cache.size() >= 8192) g_map_cache.clear();
+    g_map_cache.emplace(key, *map);
+    ++g_map_encodes;
+    return CS_OK;
+}
+
+// 2D bf16 row-major [rows, cols] with leading dimension ld; box = [box_rows, box_cols], 128B swizzle.
+static int encode_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                              int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -45,3 +94,5 @@ int make_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t co
 
 
 }  // namespace cs
+
+extern "C" int64_t cs_tensor_map_encodes(void) { return (int64_t)cs::tensor_map_encode_count(); }

@@ -162,12 +162,19 @@ def layernorm_fwd(x: Tensor, M: int, D: int, gamma: Tensor, beta: Tensor, eps: f
     return out
 
 
+def row_stats_cast(x: Tensor, M: int, D: int, xb: Tensor, stats: Tensor) -> None:
+    """f32 rows -> bf16 copy + LayerNorm partial statistics [M, parts, 2] (whole row in part 0)."""
+    _chk(x, torch.float32, "x")
+    _chk(xb, torch.bfloat16, "xb")
+    call("cs_row_stats_cast", _p(x), x.shape[-1], M, D, _p(xb), xb.shape[-1], _p(stats), stats.shape[-2], _stream())
+
+
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optional[int] = None,
          K: Optional[int] = None, mode: int = L.EPI_STORE, bias: Optional[Tensor] = None,
          residual: Optional[Tensor] = None, rope: Optional[Tuple[Tensor, Tensor]] = None, tokens: int = 0,
          rope_cols: int = 0, pos_embed: Optional[Tensor] = None, alpha: float = 1.0,
          ldo: Optional[int] = None, dbg: int = 0, ln_fold: Optional[Tuple[Tensor, Tensor, int, int, float]] = None,
-         stats_out: Optional[Tensor] = None, k_splits: int = 0) -> Tensor:
+         stats_out: Optional[Tensor] = None, k_splits: int = 0, out2: Optional[Tensor] = None) -> Tensor:
     """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16 row-major (lda/ldw = last dim)."""
     _chk(a, torch.bfloat16, "a")
     _chk(w, torch.bfloat16, "w")
@@ -194,6 +201,8 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optio
         e.ln_stats, e.ln_c1 = _p(ln_fold[0]), _p(ln_fold[1])
         e.ln_parts, e.ln_dim, e.ln_eps = int(ln_fold[2]), int(ln_fold[3]), float(ln_fold[4])
     e.stats_out = _p(stats_out)
+    if out2 is not None:             # bf16 copy of the f32 output (+ stats_out: its row statistics)
+        e.out2_bf16, e.ldo2 = _p(out2), out2.shape[-1]
     e.reserved2 = k_splits           # split-K (out must be pre-zeroed): -1 = let the library choose
     if GEMM_PROFILE is None:
         call("cs_gemm_bf16", _p(a), a.shape[-1], _p(w), w.shape[-1], M, N, K, C.byref(e), _stream())

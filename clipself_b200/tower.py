@@ -67,9 +67,16 @@ def _round_up(x: int, m: int) -> int:
 
 
 def _attention_emits_stats(tokens: int) -> bool:
-    """The LayerNorm row statistics come from the tcgen05 attention epilogues: the N <= 224 kernel, or the
-    (opt-in, CS_ATTN_LONG_TC) long-sequence kernel."""
-    return tokens <= 224 or os.environ.get("CS_ATTN_LONG_TC", "0") not in ("", "0")
+    """The LayerNorm row statistics come from the tcgen05 attention epilogues (both the N <= 224 kernel and the
+    streaming one); only the mma.sync A/B kernel (CS_ATTN_LEGACY=1) has none."""
+    return os.environ.get("CS_ATTN_LEGACY", "0") in ("", "0")
+
+
+def stat_parts(n: int) -> int:
+    """Partial (sum, sumsq) pairs per row that a GEMM epilogue writes for an n-column output: one per
+    (n-tile, column half), tiles of 256 columns when n % 256 == 0, else 128 (cs_gemm_epilogue_t.stats_out)."""
+    t = 256 if n % 256 == 0 else 128
+    return 2 * ((n + t - 1) // t)
 
 
 def chunk_schedule(rows: int, step: int) -> List[tuple]:
@@ -136,7 +143,8 @@ class PackedBlock:
     __slots__ = ("wqkv", "bqkv", "wv", "bv", "wproj", "bproj", "w12", "b12", "w3", "b3",
                  "g1", "b1", "gi", "bi", "g2", "b2", "gf", "bf",
                  # LayerNorm-folded operands (frozen weights): W*diag(gamma), rowsum(W'), W*beta + b
-                 "wproj_f", "c1_proj", "c2_proj", "w3_f", "c1_w3", "c2_w3")
+                 "wproj_f", "c1_proj", "c2_proj", "w3_f", "c1_w3", "c2_w3",
+                 "wqkv_f", "c1_qkv", "c2_qkv", "w12_f", "c1_w12", "c2_w12")
 
 
 class PackedTower:
@@ -201,6 +209,16 @@ class PackedTower:
             pb.w3_f = ops.cast_pad_bf16(w3 * pb.gf[None, :], cfg.hidden_pad)
             pb.c1_w3 = pb.w3_f.float().sum(1).contiguous()
             pb.c2_w3 = (w3 @ pb.bf + pb.b3).contiguous()
+            # norm1 folded into q|k|v, norm2 into w1|w2 (same algebra; the GEMMs then read the bf16 copy of the
+            # residual stream that the previous block's epilogue wrote, and no LayerNorm pass exists at all)
+            wqkv = torch.cat([wq, wk, wv], dim=0)
+            pb.wqkv_f = ops.cast_pad_bf16(wqkv * pb.g1[None, :])
+            pb.c1_qkv = pb.wqkv_f.float().sum(1).contiguous()
+            pb.c2_qkv = (wqkv @ pb.b1 + pb.bqkv).contiguous()
+            w1, w2 = f(p + "mlp.w1.weight"), f(p + "mlp.w2.weight")
+            pb.w12_f, pb.c2_w12 = ops.pack_swiglu_weights(w1 * pb.g2[None, :], w2 * pb.g2[None, :],
+                                                          w1 @ pb.b2 + f(p + "mlp.w1.bias"), w2 @ pb.b2 + f(p + "mlp.w2.bias"), D)
+            pb.c1_w12 = pb.w12_f.float().sum(1).contiguous()
 
 
 class Workspace:
@@ -217,7 +235,10 @@ class Workspace:
         self.h = torch.empty(rows, Hd, **bf)
         self.h2 = torch.zeros(rows, Hd, **bf)           # padded columns must stay finite (they meet zero weights)
         self.stats_att = torch.empty(rows, 2 * cfg.heads, 2, device=device, dtype=torch.float32)
-        self.stats_h = torch.empty(rows, max(Hd // 128, 1), 2, device=device, dtype=torch.float32)
+        self.stats_h = torch.empty(rows, Hd // 64, 2, device=device, dtype=torch.float32)
+        # bf16 copy of the residual stream + its row statistics (written by the proj / w3 / embed epilogues)
+        self.xb = torch.empty(rows, D, **bf)
+        self.stats_x = torch.empty(rows, stat_parts(D), 2, device=device, dtype=torch.float32)
 
 
 class TowerEngine:
@@ -238,13 +259,19 @@ class TowerEngine:
         # LayerNorm folding needs the producers' row statistics: the tcgen05 attention kernel (N <= 224)
         # and an even number of SwiGLU tiles per row
         self.fold_proj = _attention_emits_stats(cfg.tokens) and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
-        self.fold_w3 = (cfg.hidden_pad // 128) % 2 == 0 and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+        self.fold_w3 = os.environ.get("CLIPSELF_NO_LN_FOLD") is None
+        # norm1 / norm2 folded as well (CLIPSELF_NO_NORM_FOLD=1 keeps them as explicit LayerNorm kernels for A/B)
+        self.fold_norm = self.fold_proj and self.fold_w3 and os.environ.get("CLIPSELF_NO_NORM_FOLD") is None
 
         self._views: Dict[int, "TowerEngine"] = {}
+        self._graphs: Dict[tuple, object] = {}
+        self._cls_ln: Optional[Tensor] = None
+        self.use_graphs = os.environ.get("CLIPSELF_NO_GRAPH") is None
 
     def repack(self, sd: Dict[str, Tensor]) -> None:
-        self.w.repack(sd)
+        self.w.repack(sd)            # new packed tensors: captured graphs point at the old ones
         self._views.clear()
+        self._graphs.clear()
 
     def at_grid(self, grid: int) -> "TowerEngine":
         """The same tower at another input resolution (token grid): shares the packed block weights,
@@ -265,8 +292,8 @@ class TowerEngine:
             v.w.pos = rescale_pos_embed(self.w.pos_src, grid)
             v.chunk_images = max(1, self.chunk_images * self.cfg.tokens // cfg.tokens)
             v._ws = None
-            v.fold_proj = _attention_emits_stats(cfg.tokens) and os.environ.get("CLIPSELF_NO_LN_FOLD") is None
-            v.fold_w3 = self.fold_w3
+            v._graphs, v._cls_ln, v.use_graphs = {}, None, self.use_graphs
+            v.fold_proj, v.fold_w3, v.fold_norm = self.fold_proj, self.fold_w3, self.fold_norm
             v._views = {}
             self._views[grid] = v
         return v
@@ -275,26 +302,56 @@ class TowerEngine:
     def workspace(self, images: int) -> Workspace:
         rows = images * self.cfg.tokens
         if self._ws is None or self._ws.rows < rows:
+            self._graphs.clear()
             self._ws = Workspace(self.cfg, rows, self.device)
         return self._ws
 
-    def embed(self, images: Tensor, x: Tensor) -> None:
-        """patch conv as a GEMM + bias + pos_embed, CLS rows (eva_vit_model.py:350-356, 540-544)."""
+    def embed(self, images: Tensor, x: Tensor, ws: Optional[Workspace] = None) -> None:
+        """patch conv as a GEMM + bias + pos_embed, CLS rows (eva_vit_model.py:350-356, 540-544); with the fully folded
+        pipeline also the bf16 copy + row statistics of x that the first block's QKV GEMM consumes."""
         cfg, w = self.cfg, self.w
         B = images.shape[0]
         patches = ops.im2col_patches(images, cfg.patch, w.k_pe_pad)
         ops.gemm(patches, w.pe_w, x, M=B * (cfg.tokens - 1), N=cfg.width, K=w.k_pe_pad, mode=L.EPI_TOKENS,
                  bias=w.pe_b, pos_embed=w.pos, tokens=cfg.tokens)
         ops.fill_cls_rows(w.cls, w.pos, x[:B * cfg.tokens].view(B, cfg.tokens, cfg.width))
+        if ws is not None and self.fold_norm:
+            ops.row_stats_cast(x, B * cfg.tokens, cfg.width, ws.xb, ws.stats_x)
 
     def block_inplace(self, i: int, ws: Workspace, B: int, with_attention: bool = True) -> None:
-        """One residual block on ws.x in place (inference; nothing saved)."""
+        """One residual block on ws.x in place (inference; nothing saved).
+
+        Fully folded form (default), 5 launches and no LayerNorm pass:
+            qkv  = rope(LN1-fold(xb Wqkv'^T))                       xb = bf16(x), statistics of x from the producer
+            att  = softmax(q k^T / 8) v                             (+ row statistics of att)
+            x   += LNi-fold(att Wproj'^T)        -> x, xb, stats_x  (one epilogue)
+            h    = silu(.)*(.) of LN2-fold(xb W12'^T)               (+ row statistics of h)
+            x   += LNf-fold(h W3'^T)             -> x, xb, stats_x
+        """
         cfg, pb = self.cfg, self.w.blocks[i]
         D, N = cfg.width, cfg.tokens
         M = B * N
         x, u = ws.x, ws.u
-        ops.layernorm_fwd(x, M, D, pb.g1, pb.b1, cfg.ln_eps, u)
+        eps = cfg.ln_eps
         fold_proj = with_attention and self.fold_proj
+        if self.fold_norm:
+            sx = (ws.stats_x, stat_parts(D), D, eps)
+            if with_attention:
+                ops.gemm(ws.xb, pb.wqkv_f, ws.qkv, M=M, mode=L.EPI_QKV_ROPE, bias=pb.c2_qkv, rope=(self.w.rope_pos, self.w.rope_freq),
+                         tokens=N, rope_cols=2 * D, ln_fold=(sx[0], pb.c1_qkv, *sx[1:]))
+                ops.attention_fwd(ws.qkv, B, N, cfg.heads, self.scale, ws.att, row_stats=ws.stats_att)
+                ops.gemm(ws.att, pb.wproj_f, x, M=M, bias=pb.c2_proj, residual=x, out2=ws.xb, stats_out=ws.stats_x,
+                         ln_fold=(ws.stats_att, pb.c1_proj, 2 * cfg.heads, D, eps))
+            else:       # forward_without_attn (eva_vit_model.py:317-324, 249-256): v-projection only, explicit inner LN
+                ops.gemm(ws.xb, pb.wqkv_f[2 * D:], ws.att, M=M, bias=pb.c2_qkv[2 * D:], ln_fold=(sx[0], pb.c1_qkv[2 * D:], *sx[1:]))
+                ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, eps, u)
+                ops.gemm(u, pb.wproj, x, M=M, bias=pb.bproj, residual=x, out2=ws.xb, stats_out=ws.stats_x)
+            ops.gemm(ws.xb, pb.w12_f, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.c2_w12, stats_out=ws.stats_h,
+                     ln_fold=(sx[0], pb.c1_w12, *sx[1:]))
+            ops.gemm(ws.h, pb.w3_f, x, M=M, bias=pb.c2_w3, residual=x, out2=ws.xb, stats_out=ws.stats_x,
+                     ln_fold=(ws.stats_h, pb.c1_w3, cfg.hidden_pad // 64, cfg.hidden, eps))
+            return
+        ops.layernorm_fwd(x, M, D, pb.g1, pb.b1, eps, u)
         if with_attention:
             ops.gemm(u, pb.wqkv, ws.qkv, M=M, mode=L.EPI_QKV_ROPE, bias=pb.bqkv, rope=(self.w.rope_pos, self.w.rope_freq),
                      tokens=N, rope_cols=2 * D)
@@ -303,19 +360,57 @@ class TowerEngine:
             ops.gemm(u, pb.wv, ws.att, M=M, bias=pb.bv)
         if fold_proj:      # inner_attn_ln folded into the proj GEMM's epilogue
             ops.gemm(ws.att, pb.wproj_f, x, M=M, bias=pb.c2_proj, residual=x,
-                     ln_fold=(ws.stats_att, pb.c1_proj, 2 * cfg.heads, D, cfg.ln_eps))
+                     ln_fold=(ws.stats_att, pb.c1_proj, 2 * cfg.heads, D, eps))
         else:
-            ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, cfg.ln_eps, u)
+            ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, eps, u)
             ops.gemm(u, pb.wproj, x, M=M, bias=pb.bproj, residual=x)
-        ops.layernorm_fwd(x, M, D, pb.g2, pb.b2, cfg.ln_eps, u)
+        ops.layernorm_fwd(x, M, D, pb.g2, pb.b2, eps, u)
         if self.fold_w3:   # ffn_ln folded into the w3 GEMM's epilogue
             ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12, stats_out=ws.stats_h)
             ops.gemm(ws.h, pb.w3_f, x, M=M, bias=pb.c2_w3, residual=x,
-                     ln_fold=(ws.stats_h, pb.c1_w3, cfg.hidden_pad // 128, cfg.hidden, cfg.ln_eps))
+                     ln_fold=(ws.stats_h, pb.c1_w3, cfg.hidden_pad // 64, cfg.hidden, eps))
         else:
             ops.gemm(u, pb.w12, ws.h, M=M, mode=L.EPI_SWIGLU, bias=pb.b12)
-            ops.layernorm_fwd(ws.h, M, cfg.hidden, pb.gf, pb.bf, cfg.ln_eps, ws.h2)
+            ops.layernorm_fwd(ws.h, M, cfg.hidden, pb.gf, pb.bf, eps, ws.h2)
             ops.gemm(ws.h2, pb.w3, x, M=M, bias=pb.b3, residual=x)
+
+    # ------------------------------------------------------------------ teacher
+    def _cls_chunk(self, images: Tensor, n: int, ws: Workspace, cls_ln: Tensor, out: Tensor) -> None:
+        """The kernel sequence of one teacher chunk: n crops -> out [n, embed_dim]."""
+        cfg = self.cfg
+        self.embed(images, ws.x, ws)
+        for i in range(cfg.layers):
+            self.block_inplace(i, ws, n)
+        ops.layernorm_fwd(ws.x, n, cfg.width, self.w.norm_g, self.w.norm_b, cfg.ln_eps, cls_ln, row_mul=cfg.tokens)
+        ops.gemm(cls_ln, self.w.head_w, out, M=n, bias=self.w.head_b)
+
+    def _cls_chunk_graphed(self, images: Tensor, n: int, ws: Workspace, cls_ln: Tensor, out: Tensor) -> None:
+        """Same, replayed from a CUDA graph once the (input address, chunk size) pair has been seen twice: the chunk's
+        ~65 launches (5 per block) become one graph launch, so small L2-sized chunks cost no host time.  The first call
+        of a key runs eagerly (kernel attributes / descriptor cache warm-up), the second captures.  Graphs hold raw
+        pointers: they are keyed on the input slice's address and dropped when the workspace or the weights change."""
+        if not self.use_graphs or ops.GEMM_PROFILE is not None or torch.cuda.is_current_stream_capturing():
+            return self._cls_chunk(images, n, ws, cls_ln, out)
+        key = (images.data_ptr(), n, images.dtype, ws.x.data_ptr(), cls_ln.data_ptr())
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = "seen"
+            return self._cls_chunk(images, n, ws, cls_ln, out)
+        if ent == "seen":
+            if len(self._graphs) > 256:
+                self._graphs.clear()
+            g = torch.cuda.CUDAGraph()
+            g_out = torch.empty(n, self.cfg.embed_dim, device=self.device, dtype=torch.float32)
+            l0 = L.launch_count
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.graph(g):
+                self._cls_chunk(images, n, ws, cls_ln, g_out)
+            ent = (g, g_out, L.launch_count - l0, images)        # `images` keeps the captured input storage alive
+            self._graphs[key] = ent
+        g, g_out, launches, _ = ent
+        g.replay()
+        L.launch_count += launches
+        out.copy_(g_out)
 
     # ------------------------------------------------------------------ teacher
     def forward_cls(self, images: Tensor, out: Optional[Tensor] = None, ready_events=None) -> Tensor:
@@ -326,18 +421,16 @@ class TowerEngine:
         out = out if out is not None else torch.empty(R, cfg.embed_dim, device=self.device, dtype=torch.float32)
         step = min(self.chunk_images, R)
         ws = self.workspace(step)
-        cls_ln = torch.empty(step, cfg.width, device=self.device, dtype=torch.bfloat16)
+        if self._cls_ln is None or self._cls_ln.shape[0] < step:
+            self._cls_ln = torch.empty(step, cfg.width, device=self.device, dtype=torch.bfloat16)
+        cls_ln = self._cls_ln
         pieces = chunk_schedule(R, step) if ready_events is not None else [(s, min(step, R - s)) for s in range(0, R, step)]
         if ready_events is not None:
             assert len(ready_events) == len(pieces)
         for k, (s, n) in enumerate(pieces):
             if ready_events is not None:
                 torch.cuda.current_stream().wait_event(ready_events[k])
-            self.embed(images[s:s + n], ws.x)
-            for i in range(cfg.layers):
-                self.block_inplace(i, ws, n)
-            ops.layernorm_fwd(ws.x, n, cfg.width, self.w.norm_g, self.w.norm_b, cfg.ln_eps, cls_ln, row_mul=cfg.tokens)
-            ops.gemm(cls_ln, self.w.head_w, out[s:s + n], M=n, bias=self.w.head_b)
+            self._cls_chunk_graphed(images[s:s + n], n, ws, cls_ln, out[s:s + n])
         return out
 
     # ------------------------------------------------------------------ student (inference)
@@ -351,7 +444,7 @@ class TowerEngine:
         ws = self.workspace(step)
         for s in range(0, B, step):
             n = min(step, B - s)
-            self.embed(images[s:s + n], ws.x)
+            self.embed(images[s:s + n], ws.x, ws)
             for i in range(cfg.layers - 1):
                 self.block_inplace(i, ws, n)
             self.block_inplace(cfg.layers - 1, ws, n, with_attention=False)

@@ -38,6 +38,9 @@ int cs_abi_version(void);
 /* Fills sm (e.g. 100), SM count, and total HBM bytes of the current device; CS_ERR_CUDA if no
  * usable sm_100 device is present (the product path must fail loudly, never fall back). */
 int cs_device_info(int* sm_out, int* num_sms_out, int64_t* hbm_bytes_out);
+/* Number of cuTensorMapEncodeTiled driver calls made so far by this process (TMA descriptors are cached per
+ * (address, geometry): a steady-state step makes none). */
+int64_t cs_tensor_map_encodes(void);
 
 /* ------------------------------------------------------------------------------------------
  * Region path (HBM-bound, no tensor cores)
@@ -148,6 +151,13 @@ int cs_layernorm_fwd(const void* x, cs_dtype_t x_dtype, int64_t ldx, int64_t M, 
                      const float* gamma, const float* beta, float eps, void* y_bf16, int64_t ldy,
                      float* mean, float* rstd, void* stream);
 
+/* x [M, ldx] f32 -> xb [M, ldb] bf16 (round to nearest even) and stats [M, parts, 2] f32 = the (sum, sum of squares)
+ * of every row in part 0, zeros in the other parts: the operands of a LayerNorm folded into the next GEMM
+ * (cs_gemm_epilogue_t.ln_stats) for a residual stream that was not produced by a GEMM epilogue (the patch embedding
+ * output, eva_vit_model.py:540-544).  D, ldx, ldb multiples of 4. */
+int cs_row_stats_cast(const float* x, int64_t ldx, int64_t M, int D, void* xb_bf16, int64_t ldb, float* stats,
+                      int parts, void* stream);
+
 /* Epilogue description of cs_gemm_bf16 (all pointers device, may be NULL when unused). */
 typedef enum {
     CS_EPI_STORE = 0,      /* out = acc + bias (+ residual)                                     */
@@ -175,8 +185,9 @@ typedef struct {
     /* LayerNorm folding (frozen teacher): the GEMM runs on the UN-normalised rows a with weights
      * W' = W*diag(gamma); the epilogue applies  y = rstd*(acc - mean*ln_c1[n]) + bias[n]  with
      * ln_c1 = rowsum(W'), bias = W*beta + b, and (mean, rstd) of each input row rebuilt from
-     * ln_parts partial (sum, sumsq) pairs:  ln_stats [M, ln_parts, 2].  STORE / f32 / in-place
-     * residual only.  NULL ln_stats disables it. */
+     * ln_parts partial (sum, sumsq) pairs:  ln_stats [M, ln_parts, 2] (ln_parts even).  Every mode
+     * but TOKENS (the folded value then goes through RoPE / SwiGLU / the residual add like a plain
+     * accumulator); alpha must be 1.  NULL ln_stats disables it. */
     const float* ln_stats;
     const float* ln_c1;      /* [N] */
     int32_t ln_parts;
@@ -184,9 +195,17 @@ typedef struct {
     float ln_eps;
     int32_t reserved2;       /* split-K: 0 = off, -1 = choose, n = n splits; partial products are red.add'ed into
                               * `out`, which must be zero on entry (f32 STORE, no residual) */
-    /* SWIGLU only, optional: per (row, 256-wide tile) partial (sum, sumsq) of the bf16 outputs:
-     * stats_out [M, N/256, 2] — the ln_stats of the following w3 GEMM (ffn_ln folded). */
+    /* Row statistics for a LayerNorm folded into the NEXT GEMM: partial (sum, sumsq) of the f32 output values
+     * per (row, n-tile, column half of the tile)  ->  stats_out [M, 2*ceil(N/T), 2], T = 256 if N % 256 == 0 else 128
+     * (SWIGLU: T = 256 packed columns = 128 outputs; the statistics are over the outputs).  Produced by the
+     * SWIGLU epilogue (ffn_ln folded into w3) and by the out2_bf16 epilogue (norm1 / norm2 folded into the
+     * qkv / w1|w2 GEMMs).  Optional. */
     float* stats_out;
+    /* STORE / f32 / residual only, optional: additionally write the output rounded to bf16
+     * (out2_bf16 [M, ldo2]) — the new residual stream as the next GEMM's A operand, so no separate
+     * LayerNorm / cast pass reads the f32 stream again. */
+    void* out2_bf16;
+    int64_t ldo2;
 } cs_gemm_epilogue_t;
 
 /* C[M,N] = A[M,K] · W[N,K]^T on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM ->

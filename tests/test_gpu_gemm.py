@@ -179,9 +179,113 @@ def test_gemm_swiglu_stats(dev):
     a = torch.randn(M, D, generator=g).to(torch.bfloat16).to(dev)
     packed, b12 = ops.pack_swiglu_weights(w1, w2, b1, b2, D)
     out = torch.empty(M, Hd, device=dev, dtype=torch.bfloat16)
-    stats = torch.full((M, Hd // 128, 2), float("nan"), device=dev)
+    stats = torch.full((M, Hd // 64, 2), float("nan"), device=dev)       # per (row, tile, column half): 64 outputs each
     ops.gemm(a, packed, out, mode=L.EPI_SWIGLU, bias=b12, stats_out=stats)
-    o = out.float().view(M, Hd // 128, 128)
+    o = out.float().view(M, Hd // 64, 64)
     # statistics are taken before the bf16 rounding of the stored values
     torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=5e-3, atol=0.15)
     torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=5e-3, atol=0.5)
+
+
+def _fold_operands(W, gamma, beta, b, ops):
+    wf = ops.cast_pad_bf16(W * gamma[None, :])
+    return wf, wf.float().sum(1).contiguous(), (W @ beta + (b if b is not None else 0)).contiguous()
+
+
+def _row_stats(x, parts):
+    M, K = x.shape
+    xf = x.float().view(M, parts, K // parts)
+    return torch.stack([xf.sum(-1), (xf * xf).sum(-1)], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 768), (260, 1024, 1024), (130, 128, 256)])
+def test_gemm_residual_emit(dev, M, N, K):
+    """x_new = x + a W^T + b written as f32 AND bf16 with per (row, tile, half) statistics (the next block's folded
+    LayerNorm operands), with and without a folded LayerNorm on the input."""
+    from clipself_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    a = (torch.randn(M, K, generator=g) * 1.3 + 0.2).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(K, generator=g)).to(dev), (0.1 * torch.randn(K, generator=g)).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    x = torch.randn(M, N, generator=g).to(dev)
+    T = 256 if N % 256 == 0 else 128
+    parts = 2 * ((N + T - 1) // T)
+    for fold in (False, True):
+        out = torch.full((M, N), float("nan"), device=dev)
+        out2 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        stats = torch.full((M, parts, 2), float("nan"), device=dev)
+        if fold:
+            wf, c1, c2 = _fold_operands(W, gamma, beta, b, ops)
+            ref = x + torch.nn.functional.layer_norm(a.float(), (K,), gamma, beta, 1e-6) @ W.to(torch.bfloat16).float().t() + b
+            ops.gemm(a, wf, out, bias=c2, residual=x, out2=out2, stats_out=stats, ln_fold=(_row_stats(a, 4), c1, 4, K, 1e-6))
+        else:
+            wb = ops.cast_pad_bf16(W)
+            ref = x + a.float() @ wb.float().t() + b
+            ops.gemm(a, wb, out, bias=b, residual=x, out2=out2, stats_out=stats)
+        ok, msg = _report(f"emit fold={fold} f32", out, ref, 1.5e-2 if fold else 2e-3)
+        assert ok, msg
+        assert torch.equal(out2, out.to(torch.bfloat16))                       # the bf16 copy is the rounded f32 output
+        o = out.view(M, parts, N // parts) if N % (parts) == 0 else None
+        if o is not None:
+            torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-4, atol=1e-3)
+            torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("D,tokens,B", [(768, 197, 3), (128, 17, 5)])
+def test_gemm_qkv_rope_ln_fold(dev, D, tokens, B):
+    """norm1 folded into the fused QKV projection: rope(LN(x) Wqkv^T + b) from the un-normalised bf16 rows."""
+    from clipself_b200 import ops, _lib as L
+    from clipself_b200.tower import rope_tables, rope_vectors
+    grid = int(round((tokens - 1) ** 0.5))
+    M, N = B * tokens, 3 * D
+    g = torch.Generator().manual_seed(12)
+    xb = (torch.randn(M, D, generator=g) * 2.0 + 0.3).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, D, generator=g) / D ** 0.5).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(D, generator=g)).to(dev), (0.1 * torch.randn(D, generator=g)).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    wf, c1, c2 = _fold_operands(W, gamma, beta, bias, ops)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(xb, wf, out, mode=L.EPI_QKV_ROPE, bias=c2, rope=tuple(t.to(dev) for t in rope_vectors(grid, 64, 16)),
+             tokens=tokens, rope_cols=2 * D, ln_fold=(_row_stats(xb, 6 if D % 6 == 0 else 4), c1, 6 if D % 6 == 0 else 4, D, 1e-6))
+    y = torch.nn.functional.layer_norm(xb.float(), (D,), gamma, beta, 1e-6) @ W.to(torch.bfloat16).float().t() + bias
+    cos, sin = (t.to(dev) for t in rope_tables(grid, 64, 16))
+    ref = y.view(B, tokens, 3, D // 64, 64).clone()
+    t = ref[:, 1:, :2]
+    pairs = t.reshape(*t.shape[:-1], 32, 2)
+    rot = torch.stack((-pairs[..., 1], pairs[..., 0]), -1).reshape(t.shape)
+    ref[:, 1:, :2] = t * cos[None, :, None, None, :] + rot * sin[None, :, None, None, :]
+    ok, msg = _report("qkv+rope+fold", out, ref.view(M, N), 1.5e-2)
+    assert ok, msg
+
+
+def test_gemm_swiglu_ln_fold(dev):
+    """norm2 folded into the packed w1|w2 GEMM with the SiLU*mul epilogue."""
+    from clipself_b200 import ops, _lib as L
+    D, Hd, M = 768, 2048, 900
+    g = torch.Generator().manual_seed(13)
+    w1, w2 = (torch.randn(Hd, D, generator=g) / D ** 0.5).to(dev), (torch.randn(Hd, D, generator=g) / D ** 0.5).to(dev)
+    b1, b2 = torch.randn(Hd, generator=g).to(dev), torch.randn(Hd, generator=g).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(D, generator=g)).to(dev), (0.1 * torch.randn(D, generator=g)).to(dev)
+    xb = (torch.randn(M, D, generator=g) * 1.5 - 0.2).to(torch.bfloat16).to(dev)
+    packed, b12 = ops.pack_swiglu_weights(w1 * gamma[None, :], w2 * gamma[None, :], w1 @ beta + b1, w2 @ beta + b2, D)
+    c1 = packed.float().sum(1).contiguous()
+    out = torch.empty(M, Hd, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(M, Hd // 64, 2, device=dev)
+    ops.gemm(xb, packed, out, mode=L.EPI_SWIGLU, bias=b12, stats_out=stats, ln_fold=(_row_stats(xb, 6), c1, 6, D, 1e-6))
+    u = torch.nn.functional.layer_norm(xb.float(), (D,), gamma, beta, 1e-6)
+    ref = torch.nn.functional.silu(u @ w1.to(torch.bfloat16).float().t() + b1) * (u @ w2.to(torch.bfloat16).float().t() + b2)
+    ok, msg = _report("swiglu+fold", out, ref, 2e-2)
+    assert ok, msg
+
+
+def test_tensor_map_cache_steady_state(dev):
+    """TMA descriptors are cached per (address, geometry): repeating a launch makes no driver encode call."""
+    from clipself_b200 import ops, _lib as L
+    a, w = _mk(300, 256, 128, dev, seed=14)
+    out = torch.empty(300, 256, device=dev)
+    ops.gemm(a, w, out)
+    n0 = L.lib().cs_tensor_map_encodes()
+    for _ in range(5):
+        ops.gemm(a, w, out)
+    assert L.lib().cs_tensor_map_encodes() == n0

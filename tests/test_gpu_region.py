@@ -153,9 +153,6 @@ def test_mask_pool_empty_mask_and_large_extract(dev):
     assert crop_index[:R].cpu().tolist() == idx_ref.tolist()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CS_TEST_EXPERIMENTAL") is None,
-                    reason="staged on-device crop generation: its arithmetic is verified on the CPU "
-                           "(tests/test_crops_emulation.py); the kernels themselves have not run yet (CS_TEST_EXPERIMENTAL=1)")
 def test_device_crops_bit_exact_vs_reference_fixture(dev, golden):
     import numpy as np
     from clipself_b200.crops import device_crops, device_det_image

@@ -105,13 +105,9 @@ def test_resize_bilinear(dev, hin, hout, dtype):
         assert torch.equal(y, x)
 
 
-@pytest.mark.skipif(os.environ.get("CS_TEST_EXPERIMENTAL") is None,
-                    reason="experimental long-sequence tcgen05 attention: opt-in (CS_TEST_EXPERIMENTAL=1), "
-                           "run it in its own process under `timeout`")
 @pytest.mark.parametrize("B,N,H", [(1, 225, 1), (2, 577, 16), (1, 1000, 2), (1, 4097, 12), (3, 129, 2)])
 def test_attention_fwd_long_tc(dev, B, N, H, monkeypatch):
     from clipself_b200 import ops
-    monkeypatch.setenv("CS_ATTN_LONG_TC", "1")
     D = H * 64
     torch.manual_seed(7 * N + H)
     qkv = torch.randn(B * N, 3 * D, device=dev).to(torch.bfloat16)

@@ -302,8 +302,6 @@ def test_repeated_backward_does_not_double_gradients():
         assert abs(a - b) <= 1e-3 * a, norms
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CS_TEST_EXPERIMENTAL") is None,
-                    reason="added after the round-1 GPU budget was spent: opt-in until it has run once (CS_TEST_EXPERIMENTAL=1)")
 def test_eval_loop_shared_dense_pass(golden):
     """encode_boxes_and_masks == (encode_pseudo_boxes, encode_masks), and the region-classification loop runs."""
     import types as _t

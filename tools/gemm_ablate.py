@@ -9,7 +9,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 M = 128 * 197
 
 
-def run(name, N, K, mode, odt, res, dbg):
+def run(name, N, K, mode, odt, res, dbg, fold=False, emit=False):
     a = torch.randn(M, K, device=dev).to(torch.bfloat16)
     w = torch.randn(N, K, device=dev).to(torch.bfloat16)
     bias = torch.randn(N, device=dev)
@@ -21,6 +21,13 @@ def run(name, N, K, mode, odt, res, dbg):
         kw.update(residual=torch.zeros_like(out))
     if res == 2:
         kw.update(residual=out)
+    if fold:
+        kw.update(ln_fold=(torch.rand(M, 6, 2, device=dev) + 1.0, torch.randn(N, device=dev), 6, K, 1e-6))
+    if emit:
+        kw.update(residual=out, out2=torch.empty(M, N, device=dev, dtype=torch.bfloat16),
+                  stats_out=torch.empty(M, 2 * ((N + 255) // 256), 2, device=dev))
+    if mode == L.EPI_SWIGLU:
+        kw.update(stats_out=torch.empty(M, N // 128, 2, device=dev))
     ts = []
     for i in range(7):
         flush.zero_()
@@ -32,6 +39,11 @@ def run(name, N, K, mode, odt, res, dbg):
     print(f"{name:28s} dbg={dbg:2d} {t*1e3:8.1f} us {2.0*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)
 
 
+import sys as _s
+if len(_s.argv) > 1 and _s.argv[1] == "bits":
+    for dbg in (0, 1, 2, 4, 5, 6, 8):
+        run("w12 store bf16 N=4096", 4096, 768, L.EPI_STORE, torch.bfloat16, 0, dbg)
+    _s.exit(0)
 for dbg in (0, 8):
     run("w12 store bf16 N=4096", 4096, 768, L.EPI_STORE, torch.bfloat16, 0, dbg)
     run("qkv rope bf16 N=2304", 2304, 768, L.EPI_QKV_ROPE, torch.bfloat16, 0, dbg)
@@ -40,3 +52,7 @@ for dbg in (0, 8):
     run("proj res-load f32 N=768", 768, 768, L.EPI_STORE, torch.float32, 1, dbg)
     run("w3 red f32 N=768 K=2048", 768, 2048, L.EPI_STORE, torch.float32, 2, dbg)
     run("store f32 N=768 K=768", 768, 768, L.EPI_STORE, torch.float32, 0, dbg)
+    run("qkv rope fold N=2304", 2304, 768, L.EPI_QKV_ROPE, torch.bfloat16, 0, dbg, fold=True)
+    run("swiglu fold N=4096", 4096, 768, L.EPI_SWIGLU, torch.bfloat16, 0, dbg, fold=True)
+    run("proj fold emit N=768", 768, 768, L.EPI_STORE, torch.float32, 0, dbg, fold=True, emit=True)
+    run("w3 fold emit N=768 K=2048", 768, 2048, L.EPI_STORE, torch.float32, 0, dbg, fold=True, emit=True)
