@@ -123,3 +123,54 @@ def test_forward_l14_336(golden):
     np.testing.assert_allclose(out["teacher"].numpy(), g["teacher"], rtol=5e-4, atol=1e-4)
     np.testing.assert_allclose(out["dense"].numpy(), g["dense_nhwc"], rtol=5e-4, atol=1e-5)
     np.testing.assert_allclose(out["loss"].item(), float(g["loss"]), rtol=2e-5)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-arithmetic oracle (oracle/device_arith_oracle.py): anchored on the fp32 oracle above
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fold", [True, False])
+def test_device_arith_oracle_reduces_to_the_fp32_oracle(fold):
+    """With every rounding point disabled the device-arithmetic restatement (folded and explicit LayerNorm forms) is the
+    fp32 oracle, which the reference fixtures pin."""
+    from oracle import device_arith_oracle as DA
+    cfg = O.CFG_TINY
+    sd = O.synth_tower_weights(cfg, 5)
+    images, boxes, crops = O.synth_batch(cfg, 2, 4, 6, kind="proposal", ragged=True)
+    with torch.no_grad():
+        a = DA.tower_forward_cls(sd, crops.flatten(0, 1), cfg, fold=fold, exact=True)
+        b = O.tower_forward_cls(sd, crops.flatten(0, 1), cfg)
+        torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-6)
+        a = DA.tower_encode_dense(sd, images, cfg, fold=fold, exact=True)
+        b = O.tower_encode_dense(sd, images, cfg)
+        torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-6)
+
+
+def test_device_arith_oracle_rounding_is_the_bf16_noise():
+    """Rounding on: the deviation from fp32 is of the size of the reference's own bf16-autocast deviation (the yardstick
+    stored in the fixtures), i.e. the rounding points are neither missing nor doubled."""
+    from oracle import device_arith_oracle as DA
+    cfg = O.CFG_TINY
+    sd = O.synth_tower_weights(cfg, 5)
+    images, _, _ = O.synth_batch(cfg, 2, 4, 6, kind="proposal", ragged=True)
+    with torch.no_grad():
+        ref = O.tower_encode_dense(sd, images, cfg)
+        for fold in (True, False):
+            got = DA.tower_encode_dense(sd, images, cfg, fold=fold)
+            r = ((got - ref).norm() / ref.norm()).item()
+            assert 5e-4 < r < 2e-2, (fold, r)
+
+
+def test_device_arith_oracle_step_gradients_flow():
+    from oracle import device_arith_oracle as DA
+    cfg = O.CFG_TINY
+    ssd, tsd = O.synth_tower_weights(cfg, 7), O.synth_tower_weights(cfg, 8)
+    for k, v in ssd.items():
+        if k.startswith("blocks."):
+            v.requires_grad_(True)
+    batch = O.synth_batch(cfg, 2, 4, 9, kind="grid")
+    out = DA.clipself_step(ssd, tsd, *batch, cfg)
+    out["loss"].backward()
+    ref = O.clipself_step({k: v.detach() for k, v in ssd.items()}, tsd, *batch, cfg)
+    assert abs(out["loss"].item() - ref["loss"].item()) < 5e-3 * abs(ref["loss"].item())
+    assert ssd["blocks.0.mlp.w3.weight"].grad.abs().sum() > 0
+    assert ssd[f"blocks.{cfg.layers - 1}.attn.q_proj.weight"].grad is None      # grad-less in the reference too (SURVEY a15)
