@@ -128,6 +128,27 @@ def synth_host_batch(cfg, B, K, kind, seed, det=None):
     return images.pin_memory(), boxes.pin_memory(), crops.pin_memory()
 
 
+def synth_raw_image_batch(cfg, B, K, seed, det=None, hw=(480, 640)):
+    """The image-backed form of the same workload: B decoded uint8 images (COCO-like 480 x 640) with K cells of the 6 x 6
+    (8 x 8 for K > 36) grid of GridDistillDataset each; the crops and the student images are made on the device."""
+    import random
+    from clipself_b200.crops import RawImageBatch, grid_sample_boxes
+    side = 6 if K <= 36 else 8
+    g = torch.Generator().manual_seed(seed)
+    rng = random.Random(seed)
+    images, px, templates = [], [], []
+    for _ in range(B):
+        images.append(torch.randint(0, 256, (hw[0], hw[1], 3), generator=g, dtype=torch.uint8))
+        idx = list(range(side * side))
+        rng.shuffle(idx)
+        p, t = grid_sample_boxes(hw[0], hw[1], (side, side), idx, K, det or cfg.image_size)
+        px.append(p)
+        templates.append(t)
+    raw = RawImageBatch(images, px, torch.stack(templates), det or cfg.image_size, cfg.image_size)
+    raw.prepare()             # what the DataLoader's collate does: pinned uint8 blob + integer crop descriptors
+    return raw
+
+
 def run_b200(args):
     import torch.distributed as dist
     from clipself_b200 import _lib, ops
@@ -241,6 +262,19 @@ def run_b200(args):
     torch.cuda.synchronize()
     h2d_gbs = host_batch[2].numel() * 4 / c0.elapsed_time(c1) / 1e6
 
+    # the same step fed by an image-backed dataset: B uint8 images cross PCIe, crops + student images are made on the device
+    dev_crops = None
+    if wl["kind"] == "grid" and not wl.get("mask_pool"):
+        raw_batch = synth_raw_image_batch(cfg, B, K, seed=4321 + rank, det=wl.get("det"))
+        for _ in range(3):
+            step(raw_batch)
+        dc_ms, _ = timed(raw_batch, args.steps, read_loss=True)
+        dev_crops = {"value": round(world * B / (dc_ms / args.steps / 1e3), 2), "unit": "images/sec",
+                     "h2d_bytes_per_step": int(raw_batch.host_bytes()), "d2h_bytes_per_step": 4,
+                     "ms_per_step": round(dc_ms / args.steps, 3),
+                     "input": "decoded uint8 480x640 images + grid boxes; K bicubic crops/img and the student image made on the GPU "
+                              "(bit-exact with the reference's PIL transforms)"}
+
     # roofline of the dominant kernel: event-time every GEMM launch of one more step
     ops.GEMM_PROFILE = []
     step(dev_batch)
@@ -284,6 +318,7 @@ def run_b200(args):
                    "last_loss": float(last_loss.detach())},
         "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_copy_alone_gbs": round(h2d_gbs, 1)},
+        "e2e_device_crops": dev_crops,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "cs::gemm::gemm_kernel (tcgen05)", "achieved": round(achieved, 1),

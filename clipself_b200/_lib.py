@@ -44,6 +44,8 @@ PROTOTYPES = {
     "cs_crop_workspace_bytes": [i32, i32, i32, i32, C.POINTER(C.c_int64)],
     "cs_crop_resize_normalize": [vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
                                  i64, vp],
+    "cs_crop_resize_normalize_batched": [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp,
+                                         vp, i64, vp],
     "cs_im2col_patches": [vp, i32, i32, i32, i32, vp, i64, vp],
     "cs_resize_bilinear": [vp, i32, i64, i32, i32, i32, i32, vp, vp],
     "cs_fill_cls_rows": [vp, vp, i32, i32, i32, vp, vp],
@@ -64,6 +66,23 @@ PROTOTYPES = {
 }
 
 _lib = None
+
+
+class TowerCfgC(C.Structure):
+    """cs_tower_cfg_t"""
+    _fields_ = [(n, C.c_int32) for n in ("image_size", "patch", "width", "heads", "layers", "hidden", "embed_dim", "pt_seq_len")] + \
+               [("ln_eps", f32)]
+
+
+PROTOTYPES.update({
+    "cs_pack_weights_bytes": [C.POINTER(TowerCfgC), C.POINTER(i64)],
+    "cs_pack_weights_create": [C.POINTER(TowerCfgC), C.POINTER(C.c_char_p), C.POINTER(vp), i32, vp, i64, vp, C.POINTER(vp)],
+    "cs_pack_weights_update": [vp, C.POINTER(C.c_char_p), C.POINTER(vp), i32, vp],
+    "cs_pack_weights_destroy": [vp],
+    "cs_query_workspace": [C.POINTER(TowerCfgC), i32, i32, C.POINTER(i64)],
+    "cs_vit_forward_cls": [vp, vp, i32, i32, vp, i64, i32, vp, vp],
+    "cs_vit_forward_dense": [vp, vp, i32, i32, i32, vp, vp, i64, i32, vp, vp],
+})
 
 
 class ClipselfB200Error(RuntimeError):
@@ -94,8 +113,11 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched by one successful call of each entry point (for bench.py's `gpu_launches`)
-KERNELS_PER_CALL = {"cs_roi_align_fwd": 2, "cs_cosine_loss_fwd": 2, "cs_col_reduce": 2, "cs_attention_bwd": 3,
-                    "cs_abi_version": 0, "cs_device_info": 0}
+KERNELS_PER_CALL = {"cs_crop_resize_normalize": 3, "cs_crop_resize_normalize_batched": 3, "cs_crop_workspace_bytes": 0,
+                    "cs_roi_align_fwd": 2, "cs_cosine_loss_fwd": 2, "cs_col_reduce": 2, "cs_attention_bwd": 3,
+                    "cs_abi_version": 0, "cs_device_info": 0, "cs_pack_weights_bytes": 0, "cs_query_workspace": 0,
+                    "cs_pack_weights_destroy": 0, "cs_pack_weights_create": 0, "cs_pack_weights_update": 0,
+                    "cs_vit_forward_cls": 0, "cs_vit_forward_dense": 0}       # tower calls: counted by the caller
 launch_count = 0
 
 

@@ -1,6 +1,6 @@
-// On-device crop generation — STAGED: written against the bit-exact CPU oracle
-// (oracle/crops_oracle.py, pinned to Pillow and to the reference's transform objects) but not yet run on
-// hardware; its GPU tests are opt-in (CS_TEST_EXPERIMENTAL=1).
+// On-device crop generation, bit-exact on a B200 against the CPU oracle
+// (oracle/crops_oracle.py, pinned to Pillow and to the reference's transform objects) and the reference-generated
+// fixtures (tests/test_gpu_region.py).
 //
 // Replaces the CPU PIL path of the distill datasets: GridDistillDataset._obtain_image_crops
 // (src/training/data.py:226-245: image.crop(box) -> transforms[1]) with
@@ -34,12 +34,22 @@ __global__ void crop_coeffs_kernel(const Desc* __restrict__ descs, int size, int
 }
 
 // horizontal pass: tmp[k][t][xx][c] for source rows ybox_first + t;  grid (row chunks, K)
-__global__ void crop_horizontal_kernel(const uint8_t* __restrict__ image, int H, int W, const Desc* __restrict__ descs,
+// A batch of crops may come from several images packed in one uint8 blob: desc_image[k] selects the image of crop k,
+// image_offsets / image_hw its byte offset and (H, W).  desc_image == nullptr: one image (H, W) at `image`.
+__global__ void crop_horizontal_kernel(const uint8_t* __restrict__ image, int H, int W, const int* __restrict__ desc_image,
+                                       const long long* __restrict__ image_offsets, const int* __restrict__ image_hw,
+                                       const Desc* __restrict__ descs,
                                        int size, int ksize_max, int tmp_rows_max, const int* __restrict__ bounds,
                                        const int* __restrict__ kk, uint8_t* __restrict__ tmp) {
     const int k = blockIdx.y;
     const Desc d = descs[k];
     if (desc_empty(d)) return;
+    if (desc_image != nullptr) {
+        const int im = desc_image[k];
+        image += image_offsets[im];
+        H = image_hw[2 * im];
+        W = image_hw[2 * im + 1];
+    }
     const int* bh = bounds + ((long long)(k * 2 + 0) * size) * 2;
     const int* bv = bounds + ((long long)(k * 2 + 1) * size) * 2;
     const int* kh = kk + ((long long)(k * 2 + 0) * size) * ksize_max;
@@ -89,16 +99,14 @@ extern "C" int cs_crop_workspace_bytes(int K, int size, int ksize_max, int tmp_r
     return CS_OK;
 }
 
-extern "C" int cs_crop_resize_normalize(const uint8_t* image_hwc, int H, int W, const void* descs, int K, int size,
-                                        int ksize_max, int tmp_rows_max, const float* mean3, const float* std3,
-                                        float* out, void* workspace, int64_t workspace_bytes, void* stream) {
-    CS_CHECK_ARG(image_hwc && descs && mean3 && std3 && out && workspace, "cs_crop_resize_normalize: null pointer");
-    CS_CHECK_ARG(H > 0 && W > 0 && K >= 0 && size > 0 && ksize_max > 0 && tmp_rows_max >= 0, "cs_crop_resize_normalize: bad shape");
+static int crop_launch(const uint8_t* image, int H, int W, const int* desc_image, const long long* image_offsets,
+                       const int* image_hw, const void* descs, int K, int size, int ksize_max, int tmp_rows_max,
+                       const float* mean3, const float* std3, float* out, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t st) {
     int64_t need = 0;
     cs_crop_workspace_bytes(K, size, ksize_max, tmp_rows_max, &need);
     CS_CHECK_ARG(workspace_bytes >= need, "cs_crop_resize_normalize: workspace too small");
     if (K == 0) return CS_OK;
-    cudaStream_t st = (cudaStream_t)stream;
     int* bounds = (int*)workspace;
     int* kk = bounds + (int64_t)K * 2 * size * 2;
     uint8_t* tmp = (uint8_t*)(kk + (int64_t)K * 2 * size * ksize_max);
@@ -106,8 +114,8 @@ extern "C" int cs_crop_resize_normalize(const uint8_t* image_hwc, int H, int W, 
     crop_coeffs_kernel<<<dim3(K, 2), 256, 0, st>>>(d, size, ksize_max, bounds, kk);
     CS_LAUNCH_CHECK();
     const int hblocks = ceil_div((int64_t)tmp_rows_max * size * 3, 256 * 4);
-    crop_horizontal_kernel<<<dim3(hblocks > 0 ? hblocks : 1, K), 256, 0, st>>>(image_hwc, H, W, d, size, ksize_max, tmp_rows_max,
-                                                                              bounds, kk, tmp);
+    crop_horizontal_kernel<<<dim3(hblocks > 0 ? hblocks : 1, K), 256, 0, st>>>(image, H, W, desc_image, image_offsets, image_hw, d,
+                                                                              size, ksize_max, tmp_rows_max, bounds, kk, tmp);
     CS_LAUNCH_CHECK();
     const float3 mean = make_float3(mean3[0], mean3[1], mean3[2]);
     const float3 stdv = make_float3(std3[0], std3[1], std3[2]);
@@ -115,4 +123,25 @@ extern "C" int cs_crop_resize_normalize(const uint8_t* image_hwc, int H, int W, 
                                                                                                bounds, kk, tmp, mean, stdv, out);
     CS_LAUNCH_CHECK();
     return CS_OK;
+}
+
+extern "C" int cs_crop_resize_normalize(const uint8_t* image_hwc, int H, int W, const void* descs, int K, int size,
+                                        int ksize_max, int tmp_rows_max, const float* mean3, const float* std3,
+                                        float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    CS_CHECK_ARG(image_hwc && descs && mean3 && std3 && out && workspace, "cs_crop_resize_normalize: null pointer");
+    CS_CHECK_ARG(H > 0 && W > 0 && K >= 0 && size > 0 && ksize_max > 0 && tmp_rows_max >= 0, "cs_crop_resize_normalize: bad shape");
+    return crop_launch(image_hwc, H, W, nullptr, nullptr, nullptr, descs, K, size, ksize_max, tmp_rows_max, mean3, std3, out,
+                       workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cs_crop_resize_normalize_batched(const uint8_t* images_blob, const int64_t* image_offsets, const int32_t* image_hw,
+                                                const int32_t* desc_image, const void* descs, int K, int size, int ksize_max,
+                                                int tmp_rows_max, const float* mean3, const float* std3, float* out,
+                                                void* workspace, int64_t workspace_bytes, void* stream) {
+    CS_CHECK_ARG(images_blob && image_offsets && image_hw && desc_image && descs && mean3 && std3 && out && workspace,
+                 "cs_crop_resize_normalize_batched: null pointer");
+    CS_CHECK_ARG(K >= 0 && size > 0 && ksize_max > 0 && tmp_rows_max >= 0, "cs_crop_resize_normalize_batched: bad shape");
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset table type");
+    return crop_launch(images_blob, 0, 0, desc_image, reinterpret_cast<const long long*>(image_offsets), image_hw, descs, K, size,
+                       ksize_max, tmp_rows_max, mean3, std3, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }

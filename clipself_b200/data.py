@@ -106,3 +106,110 @@ class SyntheticEvalDataset(Dataset):
                 xa, ya = int(x0), int(y0)
                 masks[k, ya:max(int(-(-y1 // 1)), ya + 1), xa:max(int(-(-x1 // 1)), xa + 1)] = 1.0
         return image, boxes, crops, masks, crops.clone()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Image-backed datasets: they yield DECODED uint8 images + the boxes of GridDistillDataset (training/data.py:135-281);
+# the pixel work (K bicubic crops per image, the detector-size student image) happens on the device inside the plug-in
+# (clipself_b200/crops.py, csrc/crops.cu), bit-exact with the reference's PIL transforms.
+# ------------------------------------------------------------------------------------------------------------------
+class _GridSamples(Dataset):
+    def __init__(self, det_size: int, crop_size: int, max_boxes: int, max_split: int, crop_scale: float, seed: int):
+        from .crops import grid_choices
+        self.det_size, self.crop_size, self.max_boxes, self.crop_scale, self.seed = det_size, crop_size, max_boxes, crop_scale, seed
+        self.choices = grid_choices(max_split)
+
+    def _sample(self, image_u8: torch.Tensor, idx: int):
+        """(image_u8, crop rectangles, boxes_template) for one image: a grid is drawn and its cells shuffled with a
+        per-sample seeded RNG (the reference uses the process-global `random`, data.py:230-232, 267-268)."""
+        import random
+        from .crops import grid_sample_boxes
+        rng = random.Random(self.seed * 1000003 + idx)
+        m, n = rng.choice(self.choices)
+        indices = list(range(m * n))
+        rng.shuffle(indices)
+        px, template = grid_sample_boxes(int(image_u8.shape[0]), int(image_u8.shape[1]), (m, n), indices, self.max_boxes,
+                                         self.det_size, self.crop_scale)
+        return image_u8, px, template
+
+    def collate(self, samples):
+        from .crops import RawImageBatch
+        raw = RawImageBatch([s[0] for s in samples], [s[1] for s in samples], torch.stack([s[2] for s in samples]),
+                            self.det_size, self.crop_size)
+        raw.prepare()             # pinned blob + descriptor tables: DataLoader-side work, not the step's
+        return raw
+
+
+class SyntheticImageGridDataset(_GridSamples):
+    """Random uint8 images of a COCO-like size with GridDistillDataset's boxes (no files needed)."""
+
+    def __init__(self, det_size: int, crop_size: int, max_boxes: int, max_split: int = 6, crop_scale: float = 1.0,
+                 length: int = 4096, seed: int = 0, hw=(480, 640)):
+        super().__init__(det_size, crop_size, max_boxes, max_split, crop_scale, seed)
+        self.length, self.hw = length, hw
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(self.seed * 7919 + idx)
+        image = torch.randint(0, 256, (self.hw[0], self.hw[1], 3), generator=g, dtype=torch.uint8)
+        return self._sample(image, idx)
+
+
+class ImageGridDistillDataset(_GridSamples):
+    """`--dataset-type grid_distill` (training/data.py:135-281): images named by a COCO-style json (`images[*].file_name`,
+    or `coco_url`) under `image_root`, decoded with Pillow to uint8 [H,W,3]; unreadable or tiny images are replaced by
+    another index like the reference does (:94-97, 258-261).  `input_filename` may also be a directory: every image file
+    in it is used."""
+
+    def __init__(self, input_filename: str, image_root: str, det_size: int, crop_size: int, max_boxes: int, max_split: int = 6,
+                 crop_scale: float = 1.0, train_ratio: float = 1.0, seed: int = 0):
+        import json
+        import os
+        import random
+        super().__init__(det_size, crop_size, max_boxes, max_split, crop_scale, seed)
+        self.image_root = image_root or ""
+        if os.path.isdir(input_filename):
+            self.image_root = self.image_root or input_filename
+            names = sorted(f for f in os.listdir(input_filename) if f.lower().endswith((".jpg", ".jpeg", ".png", ".bmp", ".webp")))
+        else:
+            with open(input_filename) as f:
+                info = json.load(f)["images"]
+            names = [im["file_name"] if "file_name" in im else os.path.join(*im["coco_url"].split("/")[-2:]) for im in info]
+        if train_ratio < 1.0:
+            random.Random(seed).shuffle(names)
+            names = names[:int(len(names) * train_ratio)]
+        if not names:
+            raise RuntimeError(f"no images found in {input_filename}")
+        self.names = names
+
+    def __len__(self):
+        return len(self.names)
+
+    def read_image(self, name: str):
+        import os
+        import numpy as np
+        from PIL import Image
+        try:
+            with Image.open(os.path.join(self.image_root, name)) as im:
+                arr = np.asarray(im.convert("RGB"))
+        except Exception:                                    # noqa: BLE001  (the reference prints and resamples too)
+            print(f"Cannot load {os.path.join(self.image_root, name)}", flush=True)
+            return None
+        if arr.shape[0] < 10 or arr.shape[1] < 10:
+            print(f"Invalid image, size {arr.shape[1::-1]}", flush=True)
+            return None
+        return torch.from_numpy(np.ascontiguousarray(arr))
+
+    def __getitem__(self, idx):
+        import random
+        image = self.read_image(self.names[idx])
+        tries = 0
+        while image is None:
+            tries += 1
+            if tries > 100:
+                raise RuntimeError("no readable image found")
+            idx = random.choice(range(len(self)))
+            image = self.read_image(self.names[idx])
+        return self._sample(image, idx)

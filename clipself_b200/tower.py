@@ -221,6 +221,75 @@ class PackedTower:
             pb.c1_w12 = pb.w12_f.float().sum(1).contiguous()
 
 
+class NativeTower:
+    """Owner of a cs_tower_t handle (include/clipself_b200.h, tower level) and of the device memory it points into."""
+
+    def __init__(self, cfg: TowerCfg, sd: Dict[str, Tensor], device: torch.device):
+        import ctypes as C
+        self.cfg, self.device = cfg, device
+        self.ccfg = L.TowerCfgC(cfg.image_size, cfg.patch, cfg.width, cfg.heads, cfg.layers, cfg.hidden, cfg.embed_dim,
+                                cfg.pt_seq_len, cfg.ln_eps)
+        need = C.c_int64(0)
+        L.call("cs_pack_weights_bytes", C.byref(self.ccfg), C.byref(need))
+        self.pack = torch.empty(int(need.value), device=device, dtype=torch.uint8)
+        self.handle = C.c_void_p()
+        names, ptrs, self._keep = self._tensor_table(sd)
+        L.call("cs_pack_weights_create", C.byref(self.ccfg), names, ptrs, len(self._keep), self.pack.data_ptr(), int(need.value),
+               torch.cuda.current_stream().cuda_stream, C.byref(self.handle))
+        self._keep = None
+        self._ws: Optional[Tensor] = None
+        self._ws_key = None
+        self.launches_per_chunk = 5 * cfg.layers + 6
+
+    def _tensor_table(self, sd: Dict[str, Tensor]):
+        import ctypes as C
+        keep = [(k, v.detach().to(device=self.device, dtype=torch.float32).contiguous()) for k, v in sd.items() if "rope" not in k]
+        names = (C.c_char_p * len(keep))(*[k.encode() for k, _ in keep])
+        ptrs = (C.c_void_p * len(keep))(*[t.data_ptr() for _, t in keep])
+        return names, ptrs, keep
+
+    def update(self, sd: Dict[str, Tensor]) -> None:
+        names, ptrs, keep = self._tensor_table(sd)
+        L.call("cs_pack_weights_update", self.handle, names, ptrs, len(keep), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.current_stream().synchronize()       # `keep` (temporary f32 copies) may be freed after this
+
+    def workspace(self, chunk: int, image_size: int) -> Tensor:
+        import ctypes as C
+        key = (chunk, image_size)
+        if self._ws_key is None or self._ws_key != key:
+            need = C.c_int64(0)
+            L.call("cs_query_workspace", C.byref(self.ccfg), chunk, image_size, C.byref(need))
+            if self._ws is None or self._ws.numel() < need.value:
+                self._ws = None
+                self._ws = torch.empty(int(need.value), device=self.device, dtype=torch.uint8)
+            self._ws_key = key
+        return self._ws
+
+    def forward_cls(self, images: Tensor, out: Tensor, chunk: int) -> None:
+        assert images.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+        n = images.shape[0]
+        ws = self.workspace(chunk, self.cfg.image_size)
+        L.call("cs_vit_forward_cls", self.handle, images.data_ptr(), ops._dt(images), n, ws.data_ptr(), ws.numel(), chunk,
+               out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        L.launch_count += self.launches_per_chunk * ((n + chunk - 1) // chunk)
+
+    def forward_dense(self, images: Tensor, out: Tensor, chunk: int, image_size: int, pos: Optional[Tensor]) -> None:
+        assert images.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+        n = images.shape[0]
+        ws = self.workspace(chunk, image_size)
+        L.call("cs_vit_forward_dense", self.handle, images.data_ptr(), ops._dt(images), n, image_size,
+               pos.data_ptr() if pos is not None else None, ws.data_ptr(), ws.numel(), chunk, out.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
+        L.launch_count += (self.launches_per_chunk + 3) * ((n + chunk - 1) // chunk)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and self.handle.value:
+                L.lib().cs_pack_weights_destroy(self.handle)
+        except Exception:           # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 class Workspace:
     """Activation scratch for one forward-only chunk of `rows` token rows."""
 
@@ -267,11 +336,19 @@ class TowerEngine:
         self._graphs: Dict[tuple, object] = {}
         self._cls_ln: Optional[Tensor] = None
         self.use_graphs = os.environ.get("CLIPSELF_NO_GRAPH") is None
+        # The product path: the tower-level C ABI (csrc/tower.cu: cs_pack_weights_* / cs_vit_forward_*) packs, sequences and
+        # graph-replays the folded pipeline natively.  The Python sequencing above/below (block_inplace) is the same kernel
+        # sequence kept for the stage-wise parity tests, per-GEMM event profiling and the un-folded A/B switches.
+        self.native: Optional[NativeTower] = None
+        if self.fold_norm and os.environ.get("CLIPSELF_PY_TOWER") is None:
+            self.native = NativeTower(cfg, sd, device)
 
     def repack(self, sd: Dict[str, Tensor]) -> None:
         self.w.repack(sd)            # new packed tensors: captured graphs point at the old ones
         self._views.clear()
         self._graphs.clear()
+        if self.native is not None:
+            self.native.update(sd)
 
     def at_grid(self, grid: int) -> "TowerEngine":
         """The same tower at another input resolution (token grid): shares the packed block weights,
@@ -293,6 +370,7 @@ class TowerEngine:
             v.chunk_images = max(1, self.chunk_images * self.cfg.tokens // cfg.tokens)
             v._ws = None
             v._graphs, v._cls_ln, v.use_graphs = {}, None, self.use_graphs
+            v.native = self.native          # one handle serves every resolution (per-grid RoPE vectors are cached inside)
             v.fold_proj, v.fold_w3, v.fold_norm = self.fold_proj, self.fold_w3, self.fold_norm
             v._views = {}
             self._views[grid] = v
@@ -427,10 +505,14 @@ class TowerEngine:
         pieces = chunk_schedule(R, step) if ready_events is not None else [(s, min(step, R - s)) for s in range(0, R, step)]
         if ready_events is not None:
             assert len(ready_events) == len(pieces)
+        native = self.native is not None and ops.GEMM_PROFILE is None and cfg.grid == self.native.cfg.grid
         for k, (s, n) in enumerate(pieces):
             if ready_events is not None:
                 torch.cuda.current_stream().wait_event(ready_events[k])
-            self._cls_chunk_graphed(images[s:s + n], n, ws, cls_ln, out[s:s + n])
+            if native:
+                self.native.forward_cls(images[s:s + n], out[s:s + n], step)
+            else:
+                self._cls_chunk_graphed(images[s:s + n], n, ws, cls_ln, out[s:s + n])
         return out
 
     # ------------------------------------------------------------------ student (inference)
@@ -441,6 +523,9 @@ class TowerEngine:
         g, C = cfg.grid, cfg.embed_dim
         out = torch.empty(B, g, g, C, device=self.device, dtype=torch.float32)
         step = min(self.chunk_images, B)
+        if self.native is not None and ops.GEMM_PROFILE is None:
+            self.native.forward_dense(images, out, step, cfg.image_size, None if g == self.native.cfg.grid else self.w.pos)
+            return out
         ws = self.workspace(step)
         for s in range(0, B, step):
             n = min(step, B - s)

@@ -21,6 +21,7 @@ import random
 import torch
 
 from .. import ops
+from ..crops import RawImageBatch, _BatchCropper
 from ..model import cosine_distill_loss
 
 
@@ -31,6 +32,7 @@ class CLIPSelf:
         self._crops_free = None
         self._images_dev = None
         self._images_free = None
+        self._cropper = None
 
     def _stream_inputs(self, images, image_crops, valid, R, device, dtype, pieces):
         """Host->device copies of one step on a side stream, in the order the step consumes them: the
@@ -81,14 +83,35 @@ class CLIPSelf:
         if distributed:
             model = getattr(model, "module", model)
             dist_model = getattr(dist_model, "module", dist_model)
-        images, normed_boxes, image_crops = batch       # texts are not paired with images
         device = torch.device(device)
         dtype = cast_dtype if cast_dtype is not None else torch.float32
-        B, K = normed_boxes.shape[:2]
-
         crop_events = None
         streamed_images = False
-        if normed_boxes.device.type == "cpu":
+        raw = batch if isinstance(batch, RawImageBatch) else None
+        if raw is not None:
+            # image-backed dataset: decoded uint8 images + boxes arrive, the student images (ResizeLongest + pad) and the K
+            # teacher crops per image (crop -> ResizeMaxSize bicubic -> pad -> normalise; data.py:226-245, transform.py:26-49,
+            # 169-191) are produced on the device, bit-exact with the reference's PIL path.  Index extraction as below.
+            normed_boxes = raw.normed_boxes
+            B, K = normed_boxes.shape[:2]
+            boxes32 = normed_boxes.float()
+            valid = boxes32[:, :, 4] > 0.5
+            offsets = torch.zeros(B + 1, dtype=torch.int32)
+            offsets[1:] = valid.sum(1).cumsum(0)
+            R = int(offsets[-1])
+            assert [len(b) for b in raw.crop_boxes_px] == valid.sum(1).tolist(), "one crop rectangle per valid box"
+            rois = boxes32[valid][:, :4].contiguous().to(device, non_blocking=True)
+            offsets = offsets.to(device, non_blocking=True)
+            if self._cropper is None:
+                self._cropper = _BatchCropper()
+            images, crops = self._cropper(raw, device)
+            crops = crops.to(dtype)
+        else:
+            images, normed_boxes, image_crops = batch       # texts are not paired with images
+            B, K = normed_boxes.shape[:2]
+        if raw is not None:
+            pass                                        # images / rois / crops are on the device already
+        elif normed_boxes.device.type == "cpu":
             # host-side, bit-exact: valid = boxes[..., 4] > 0.5, image-major order (clipself.py:29-36)
             boxes32 = normed_boxes.float()
             valid = boxes32[:, :, 4] > 0.5

@@ -131,9 +131,10 @@ def main(argv=None):
                         "'scaler' in checkpoints) over bf16 tensor-core operands; there are no fp16 kernels in this library")
     if args.accum_freq != 1:
         raise AssertionError("accum_freq must be 1 (train.py:89)")
-    if args.dataset_type != "synthetic_distill":
-        raise NotImplementedError(f"--dataset-type {args.dataset_type}: the COCO/PIL data pipeline is out of scope "
-                                  "(SURVEY.md §2); use synthetic_distill")
+    if args.dataset_type not in ("synthetic_distill", "synthetic_images_distill", "grid_distill"):
+        raise NotImplementedError(f"--dataset-type {args.dataset_type}: only grid_distill (image files, crops made on the "
+                                  "device) and the synthetic_* types are built in (SURVEY.md §2: the COCO proposal / "
+                                  "RegionCLIP pipelines are out of scope)")
 
     torch.manual_seed(args.seed)
     np.random.seed(args.seed)
@@ -178,12 +179,28 @@ def main(argv=None):
 
     # student images at --det-image-size (scripts: 1024 / 896), teacher crops at the tower's own size
     # (data.py:226-245: crops are resized to args.input_size)
-    dataset = SyntheticDistillDataset(args.det_image_size, args.input_size, args.max_boxes,
-                                      kind="grid", length=max(args.batch_size * world * 8, 64), seed=args.seed)
+    collate = None
+    if args.dataset_type == "grid_distill":
+        # the reference's GridDistillDataset (data.py:135-281) with the pixel work moved to the device: the workers decode
+        # the files to uint8 and do the box arithmetic, the plug-in makes the student image and the K crops (crops.py)
+        from ..data import ImageGridDistillDataset
+        if not args.train_data:
+            raise RuntimeError("--dataset-type grid_distill needs --train-data (COCO-style json or an image directory)")
+        dataset = ImageGridDistillDataset(args.train_data, args.train_image_root, args.det_image_size, args.input_size,
+                                          args.max_boxes, args.max_split, args.crop_scale, seed=args.seed)
+        collate = dataset.collate
+    elif args.dataset_type == "synthetic_images_distill":
+        from ..data import SyntheticImageGridDataset
+        dataset = SyntheticImageGridDataset(args.det_image_size, args.input_size, args.max_boxes, args.max_split, args.crop_scale,
+                                            length=max(args.batch_size * world * 8, 64), seed=args.seed)
+        collate = dataset.collate
+    else:
+        dataset = SyntheticDistillDataset(args.det_image_size, args.input_size, args.max_boxes,
+                                          kind="grid", length=max(args.batch_size * world * 8, 64), seed=args.seed)
     sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, seed=args.seed) \
         if args.distributed else None
     loader = DataLoader(dataset, batch_size=args.batch_size, shuffle=sampler is None, sampler=sampler,
-                        num_workers=args.workers, pin_memory=True, drop_last=True)
+                        num_workers=args.workers, pin_memory=collate is None, drop_last=True, collate_fn=collate)
     val_loader = None
     if args.synthetic_eval_classes > 0:
         from ..data import SyntheticEvalDataset

@@ -23,7 +23,7 @@ def parse_args(args=None):
     p.add_argument("--train-image-root", type=str, default=None)
     p.add_argument("--val-image-root", type=str, default=None)
     p.add_argument("--dataset-type", default="grid_distill",
-                   choices=["proposals_distill", "region_clip", "grid_distill", "synthetic_distill"])
+                   choices=["proposals_distill", "region_clip", "grid_distill", "synthetic_distill", "synthetic_images_distill"])
     p.add_argument("--test-type", default="coco_panoptic")
     p.add_argument("--max-split", type=int, default=6)
     p.add_argument("--logs", type=str, default="./logs/")

@@ -99,7 +99,7 @@ int cs_l2norm_bwd(const float* y, const float* inv_norm, const float* d_y, int64
                   float* d_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Crop generation (STAGED: not yet run on hardware, see csrc/crops.cu) — replaces the CPU PIL path of
+ * Crop generation — replaces the CPU PIL path of
  * GridDistillDataset._obtain_image_crops (training/data.py:226-245: image.crop(box) -> transforms[1]) and
  * the transforms of open_clip/transform.py:26-49,119-133 (ResizeMaxSize, centre pad) / :136-191
  * (ResizeLongest, pad right/bottom), bit-exact with Pillow's bicubic ImagingResample.
@@ -119,6 +119,14 @@ int cs_crop_workspace_bytes(int K, int size, int ksize_max, int tmp_rows_max, in
 int cs_crop_resize_normalize(const uint8_t* image_hwc, int H, int W, const void* descs, int K, int size,
                              int ksize_max, int tmp_rows_max, const float* mean3, const float* std3, float* out,
                              void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same for a BATCH of images in one call (one training batch of GridDistillDataset samples, training/data.py:226-281):
+ * images_blob holds the uint8 [H_i,W_i,3] images back to back, image_offsets[i] (bytes) and image_hw[2i], image_hw[2i+1]
+ * (H_i, W_i) describe image i, desc_image[k] is the image crop k is cut from.  All tables on the device. */
+int cs_crop_resize_normalize_batched(const uint8_t* images_blob, const int64_t* image_offsets, const int32_t* image_hw,
+                                     const int32_t* desc_image, const void* descs, int K, int size, int ksize_max,
+                                     int tmp_rows_max, const float* mean3, const float* std3, float* out, void* workspace,
+                                     int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tower kernels (EVA02 ViT, eva_vit_model.py)
@@ -289,6 +297,45 @@ int cs_swiglu_bwd(const void* x12_bf16, const void* dh_bf16, int64_t M, int Hd, 
 int cs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                   double beta1, double beta2, double eps, double weight_decay, int step,
                   double grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tower level: a frozen EVA02 vision tower as one handle and one call.
+ * What a reference maintainer binds instead of EVAVisionTransformer.forward / encode_dense
+ * (eva_vit_model.py:533-623) when the tower is frozen (the CLIPSelf teacher, clipself.py:37-38, and
+ * every inference / eval call).  Kernel sequence and LayerNorm folding: csrc/tower.cu, DESIGN.md §5.2.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t image_size, patch, width, heads, layers, hidden, embed_dim, pt_seq_len;   /* CLIPVisionCfg, eva_clip/model.py:36-62 */
+    float ln_eps;                                                                     /* 1e-6, eva_clip/model.py:123 */
+} cs_tower_cfg_t;
+typedef struct cs_tower cs_tower_t;
+
+/* Bytes of device memory the packed (bf16, LayerNorm-folded) weights of one tower need. */
+int cs_pack_weights_bytes(const cs_tower_cfg_t* cfg, int64_t* bytes);
+/* Pack the tower's weights.  names[i] / tensors_f32[i]: the `visual.*` state_dict entries WITHOUT the prefix
+ * ("blocks.0.attn.q_proj.weight", "pos_embed", ...; D.1 of SURVEY.md), contiguous f32 device tensors; extra entries
+ * (rope buffers) are ignored, a missing one is an error.  pack_buffer: caller-owned device memory of
+ * cs_pack_weights_bytes() bytes, 256 B aligned, which must outlive the handle.  Synchronises `stream` once. */
+int cs_pack_weights_create(const cs_tower_cfg_t* cfg, const char* const* names, const void* const* tensors_f32, int count,
+                           void* pack_buffer, int64_t pack_bytes, void* stream, cs_tower_t** out);
+/* Re-pack after the weights changed (same buffers; CUDA graphs captured by the forward calls stay valid). */
+int cs_pack_weights_update(cs_tower_t* tower, const char* const* names, const void* const* tensors_f32, int count, void* stream);
+int cs_pack_weights_destroy(cs_tower_t* tower);
+
+/* Bytes of activation scratch for chunks of `chunk_images` images at `image_size` (0 = the tower's own size). */
+int cs_query_workspace(const cs_tower_cfg_t* cfg, int chunk_images, int image_size, int64_t* bytes);
+
+/* encode_image(normalize=False) of a frozen tower: images [n,3,S,S] (f32 or bf16, S = cfg.image_size) -> out [n, embed_dim] f32.
+ * Processed in chunks of chunk_images through the caller's workspace (256 B aligned, cs_query_workspace bytes).  The third and
+ * later calls with the same (images, workspace, out) addresses and shapes replay a CUDA graph (CLIPSELF_NO_GRAPH=1 disables). */
+int cs_vit_forward_cls(cs_tower_t* tower, const void* images, cs_dtype_t dtype, int n_images, void* workspace,
+                       int64_t workspace_bytes, int chunk_images, float* out, void* stream);
+/* encode_dense (eva_vit_model.py:588-623) without a tape: -> out NHWC [n, S/p, S/p, embed_dim] f32, unit norm per token.
+ * image_size: any multiple of the patch size up to a 64 x 64 grid (0 = native); for a non-native size the caller passes the
+ * bicubically rescaled pos_embed [1 + grid^2, width] (eva_vit_model.py:631-643), else NULL. */
+int cs_vit_forward_dense(cs_tower_t* tower, const void* images, cs_dtype_t dtype, int n_images, int image_size,
+                         const float* pos_embed_rescaled, void* workspace, int64_t workspace_bytes, int chunk_images,
+                         float* out_nhwc, void* stream);
 
 #ifdef __cplusplus
 }

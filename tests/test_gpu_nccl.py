@@ -22,9 +22,17 @@ def _worker(rank, world, port, out):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    from tests.test_gpu_step import build_model
+    from clipself_b200.model import CustomCLIP
     from clipself_b200.training.clipself import CLIPSelf
     ocfg = O.CFG_TINY
+
+    def build_model(ocfg, seed, dev):
+        vis = dict(image_size=ocfg.image_size, layers=ocfg.layers, width=ocfg.width, head_width=64,
+                   patch_size=ocfg.patch, mlp_ratio=ocfg.hidden / ocfg.width, pt_hw_seq_len=ocfg.pt_seq_len)
+        m = CustomCLIP(embed_dim=ocfg.embed_dim, vision_cfg=vis)
+        m.visual.load_state_dict(O.synth_tower_weights(ocfg, seed), strict=False)
+        return m.to(dev)
+
     student, teacher = build_model(ocfg, 41, dev), build_model(ocfg, 42, dev)          # same weights on both ranks
     student.lock_image_tower(unlocked_groups=ocfg.layers)
     student.train()

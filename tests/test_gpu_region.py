@@ -167,3 +167,44 @@ def test_device_crops_bit_exact_vs_reference_fixture(dev, golden):
     got2 = device_crops(img2, g2["boxes"], int(g2["size"])).cpu().numpy()
     ref2 = np.stack([CO.image_crop(g2["image"], b, int(g2["size"])) for b in g2["boxes"]])
     assert np.array_equal(got2, ref2)
+
+
+def test_raw_image_batch_step_equals_tensor_batch_step(dev):
+    """An image-backed batch (decoded uint8 images + GridDistillDataset boxes, crops made on the device in ONE batched call,
+    clipself_b200/crops.py) gives bit-identical student images / crops to the per-image kernels (which the reference
+    fixtures pin) and therefore the same loss as the tensor batch built from them."""
+    import types
+    from clipself_b200.crops import _BatchCropper, device_crops, device_det_image
+    from clipself_b200.data import SyntheticImageGridDataset
+    from clipself_b200.model import CustomCLIP
+    from clipself_b200.training.clipself import CLIPSelf
+    from oracle import clipself_oracle as O
+    ocfg = O.CFG_TINY
+    ds = SyntheticImageGridDataset(det_size=96, crop_size=ocfg.image_size, max_boxes=5, max_split=3, length=8, seed=3, hw=(70, 93))
+    samples = [ds[i] for i in range(3)] + [(torch.randint(0, 256, (41, 57, 3), dtype=torch.uint8),) + ds._sample(torch.zeros(41, 57, 3, dtype=torch.uint8), 7)[1:]]
+    raw = ds.collate(samples)
+    images, crops = _BatchCropper()(raw, dev)
+    ref_crops, ref_images = [], []
+    for img, px in zip(raw.images_u8, raw.crop_boxes_px):
+        ref_images.append(device_det_image(img.to(dev), raw.det_size))
+        ref_crops.append(device_crops(img.to(dev), px.tolist(), raw.crop_size))
+    assert torch.equal(images, torch.stack(ref_images)) and torch.equal(crops, torch.cat(ref_crops))
+    # the same step through the plug-in, once from the raw batch and once from the equivalent tensors
+    vis = dict(image_size=ocfg.image_size, layers=ocfg.layers, width=ocfg.width, head_width=64, patch_size=ocfg.patch,
+               mlp_ratio=ocfg.hidden / ocfg.width, pt_hw_seq_len=ocfg.pt_seq_len)
+    student, teacher = CustomCLIP(ocfg.embed_dim, vis), CustomCLIP(ocfg.embed_dim, vis)
+    student.visual.load_state_dict(O.synth_tower_weights(ocfg, 61), strict=False)
+    teacher.visual.load_state_dict(O.synth_tower_weights(ocfg, 62), strict=False)
+    student, teacher = student.to(dev), teacher.to(dev)
+    student.lock_image_tower(unlocked_groups=ocfg.layers)
+    args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+    l_raw = CLIPSelf()(raw, student, teacher, None, dev, None, False, args)[0]["loss_cosine"].item()
+    B, K = raw.normed_boxes.shape[:2]
+    crops_t = torch.zeros(B, K, 3, raw.crop_size, raw.crop_size, device=dev)
+    o = 0
+    for b in range(B):
+        k = len(raw.crop_boxes_px[b])
+        crops_t[b, :k] = crops[o:o + k]
+        o += k
+    l_tensor = CLIPSelf()((images, raw.normed_boxes.to(dev), crops_t), student, teacher, None, dev, None, False, args)[0]["loss_cosine"].item()
+    assert l_raw == l_tensor

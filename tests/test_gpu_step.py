@@ -372,3 +372,56 @@ def test_eval_loop_shared_dense_pass(golden):
     res = zero_shot.zero_shot_eval(m, {"val": DataLoader(ds, batch_size=3)}, 1, args)
     assert set(res) == {f"{p}.{t}.macc{k}" for p in ("rois", "crops", "maskpool") for t in ("thing", "stuff") for k in (1, 5)}
     assert all(0.0 <= v <= 1.0 for v in res.values())
+
+
+def test_training_cli_end_to_end(tmp_path):
+    """The reference's launch line (scripts/train_clipself_coco_image_patches_eva_vitb16.sh) on synthetic data, in process:
+    --precision amp (GradScaler protocol), --grad-clip-norm, epoch-end ensemble checkpoint with all 436 keys + scaler +
+    --save-most-recent, the region-classification eval loop, then --resume of that checkpoint on the image-backed dataset
+    type (crops made on the device)."""
+    from clipself_b200.training.main import main
+    common = ["--batch-size", "4", "--lr", "1e-5", "--wd", "0.1", "--workers", "0", "--model", "EVA02-CLIP-B-16",
+              "--pretrained", "eva", "--warmup", "2", "--zeroshot-frequency", "1", "--cache-dir", "", "--log-every-n-steps", "1",
+              "--lock-image", "--save-frequency", "1", "--lock-image-unlocked-groups", "12", "--extract-type=v2", "--name", "smoke",
+              "--downsample-factor", "16", "--det-image-size", "224", "--alpha", "0.7", "--max-boxes", "6",
+              "--train-steps-per-epoch", "3", "--logs", str(tmp_path), "--grad-clip-norm", "5.0"]
+    main(common + ["--epochs", "1", "--dataset-type", "synthetic_distill", "--precision", "amp", "--save-most-recent",
+                   "--synthetic-eval-classes", "5"])
+    ck = tmp_path / "smoke" / "checkpoints"
+    ckpt = torch.load(ck / "epoch_1.pt", map_location="cpu")
+    assert (ck / "epoch_latest.pt").exists() and ckpt["epoch"] == 1
+    assert len(ckpt["state_dict"]) == 436 and "scaler" in ckpt and ckpt["scaler"]["scale"] == 65536.0
+    assert int(ckpt["optimizer"]["step"]) == 3
+    main(common + ["--epochs", "2", "--dataset-type", "synthetic_images_distill", "--precision", "amp_bf16", "--max-split", "3",
+                   "--resume", str(ck / "epoch_1.pt")])
+    ckpt2 = torch.load(ck / "epoch_2.pt", map_location="cpu")
+    assert ckpt2["epoch"] == 2 and int(ckpt2["optimizer"]["step"]) == 6 and "scaler" not in ckpt2
+    k = "visual.blocks.3.mlp.w1.weight"
+    assert not torch.equal(ckpt["state_dict"][k], ckpt2["state_dict"][k])           # the resumed epoch trained
+    assert torch.equal(ckpt["state_dict"]["text.token_embedding.weight"], ckpt2["state_dict"]["text.token_embedding.weight"])
+
+
+def test_eval_after_fused_steps_uses_the_updated_weights():
+    """the forward-only pack must follow FusedAdamW updates (they bypass torch's version counters)."""
+    from clipself_b200.optim import FusedAdamW
+    from clipself_b200.training.clipself import CLIPSelf
+    ocfg = O.CFG_TINY
+    dev = torch.device("cuda")
+    student, teacher = build_model(ocfg, 71, dev), build_model(ocfg, 72, dev)
+    student.lock_image_tower(unlocked_groups=ocfg.layers)
+    batch = O.synth_batch(ocfg, 2, 4, 73, kind="grid")
+    args = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+    images = batch[0].to(dev)
+    with torch.no_grad():
+        before = student.encode_dense(images, keep_shape=False).clone()
+    losses, _, _ = CLIPSelf()(batch, student, teacher, None, dev, None, False, args)
+    losses["loss_cosine"].backward()
+    opt = FusedAdamW(student.visual._student, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    opt.step()
+    with torch.no_grad():
+        after = student.encode_dense(images, keep_shape=False).clone()
+        fresh = build_model(ocfg, 71, dev)
+        fresh.load_state_dict(student.state_dict())
+        expect = fresh.encode_dense(images, keep_shape=False)
+    assert not torch.equal(before, after)
+    assert torch.equal(after, expect)
