@@ -176,6 +176,8 @@ def run_b200(args):
     host_batch = synth_host_batch(cfg, B, K, wl["kind"], seed=1234 + rank, det=wl.get("det"))
     dev_batch = tuple(t.to(device) for t in host_batch)
     method = CLIPSelf()
+    # N > 1: the gradient all-reduce and the fused AdamW run on a side stream under the next step's teacher forward
+    student.visual.overlap_gradient_sync = distributed and os.environ.get("CLIPSELF_NO_OVERLAP") is None
     margs = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
     opt = None
 
@@ -219,6 +221,8 @@ def run_b200(args):
             last = step(batch)
             if read_loss:
                 last = last.item()            # D2H read of the step's result, every step
+        if student.visual._student is not None:
+            student.visual._student.wait_weights()      # the last step's side-stream all-reduce + AdamW belong to the timed region
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0

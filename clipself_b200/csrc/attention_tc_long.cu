@@ -51,7 +51,7 @@ struct Params {
     float scale_log2, scale;
     __nv_bfloat16* out;
     float* lse;
-    float* row_stats;   // optional [B*N, 2H, 2]: per (row, head, dim-half) sum and sum of squares of the f32 output
+    float* row_stats;   // optional [B*N, 4H, 2]: per (row, head, 16-dim quarter) sum and sum of squares of the f32 output
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -297,17 +297,17 @@ attention_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap map, const Para
                     pk.w = pack_bf16(o_run[8 * i + 6] * inv, o_run[8 * i + 7] * inv);
                     *reinterpret_cast<uint4*>(dst + 8 * i) = pk;
                 }
-                if (p.row_stats != nullptr) {                       // statistics for the folded inner_attn_ln
+                if (p.row_stats != nullptr) {                       // statistics for the folded inner_attn_ln: 4 parts per head
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
+                    for (int hh = 0; hh < 4; ++hh) {
                         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float f = o_run[hh * 32 + i] * inv;
+                        for (int i = 0; i < 16; ++i) {
+                            const float f = o_run[hh * 16 + i] * inv;
                             s1 += f;
                             s2 = fmaf(f, f, s2);
                         }
-                        *reinterpret_cast<float2*>(p.row_stats + (((long long)b * p.N + row) * (2 * p.H) + 2 * h + hh) * 2) =
+                        *reinterpret_cast<float2*>(p.row_stats + (((long long)b * p.N + row) * (4 * p.H) + 4 * h + hh) * 2) =
                             make_float2(s1, s2);
                     }
                 }

@@ -47,6 +47,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Spinning variant (mbarrier.test_wait, no hardware suspend): lowest wake-up latency, for short handshakes on the critical path.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    if (mbar_test_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_test_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("clipself_b200: mbarrier spin wait timed out (smem 0x%x parity %u block %d thread %d)\n", bar, parity,
+                   (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
                                             int c_inner, int c_outer) {
     asm volatile(

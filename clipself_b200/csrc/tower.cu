@@ -290,7 +290,7 @@ static int64_t carve_ws(const Cfg& g, int images, int grid, uint8_t* base, Works
     o.u = c.take<__nv_bfloat16>(rows * D);
     o.h = c.take<__nv_bfloat16>(rows * Hp);
     o.stats_x = c.take<float>(rows * stat_parts(D) * 2);
-    o.stats_att = c.take<float>(rows * 2 * g.heads * 2);
+    o.stats_att = c.take<float>(rows * 4 * g.heads * 2);
     o.stats_h = c.take<float>(rows * (Hp / 64) * 2);
     o.patches = c.take<__nv_bfloat16>((int64_t)images * (N - 1) * g.k_pe_pad());
     o.cls_ln = c.take<__nv_bfloat16>((int64_t)images * D);
@@ -369,7 +369,7 @@ static int block(const cs_tower* t, const GridCtx& gc, int grid, int i, int n, c
         cs_gemm_epilogue_t p = epi0();
         emit_x(p);
         p.bias = b.c2_proj;
-        fold(p, w.stats_att, b.c1_proj, 2 * g.heads, D);
+        fold(p, w.stats_att, b.c1_proj, 4 * g.heads, D);
         if ((rc = cs_gemm_bf16(w.att, D, b.wproj_f, D, M, D, D, &p, st))) return rc;
     } else {        // forward_without_attn (eva_vit_model.py:317-324, 249-256): v-projection, explicit inner LN, proj
         cs_gemm_epilogue_t e = epi0();

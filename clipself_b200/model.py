@@ -127,8 +127,12 @@ class _RoiFeatures(torch.autograd.Function):
         d_dense = ops.roi_align_bwd(d_out.contiguous(), ctx.shape, img_offsets, ctx.R, wy, wx)
         eng.backward(d_dense)
         if visual.sync_gradients:
-            # the ONE collective of the step: mean all-reduce of the flat student gradient (NCCL/NVLink)
-            allreduce_flat_gradient(eng.flat_grad, eng.layout, eng.first_trainable)
+            # the ONE collective of the step: mean all-reduce of the flat student gradient (NCCL/NVLink); with
+            # overlap_gradient_sync on a side stream, so that the next step's teacher forward hides it
+            if visual.overlap_gradient_sync:
+                eng.allreduce_async()
+            else:
+                allreduce_flat_gradient(eng.flat_grad, eng.layout, eng.first_trainable)
         grads = _flat_grad_outputs(visual, eng)
         return (None, None, None, None, None, *grads)
 
@@ -196,6 +200,10 @@ class EVAVisionTransformer(nn.Module):
         self.head = nn.Linear(embed_dim, num_classes)
         self.grad_checkpointing = False
         self.sync_gradients = False          # set by the CLIPSelf plug-in when `distributed`
+        # opt-in (training CLI / bench, which step with FusedAdamW): gradient all-reduce + optimizer on a side stream,
+        # overlapped with the next step's teacher forward.  Off by default: a caller that reads `.grad` right after
+        # backward() on its own stream would otherwise have to call visual._student.wait_gradients() first.
+        self.overlap_gradient_sync = False
         self._student: Optional[StudentEngine] = None
         self._infer: Optional[TowerEngine] = None
         self._infer_version = None

@@ -31,6 +31,16 @@ class FusedAdamW:
         return None          # the backward overwrites the flat gradient buffer every step
 
     def step(self, grad_scale: float = 1.0) -> None:
+        e = self.engine
+        if e.grads_ready is not None and e.comm_stream is not None:
+            # gradients are being all-reduced on the side stream: update there, right behind the collective
+            with torch.cuda.stream(e.comm_stream):
+                self._step(grad_scale)
+                e.weights_ready = e.comm_stream.record_event()
+            return
+        self._step(grad_scale)
+
+    def _step(self, grad_scale: float) -> None:
         e, lay = self.engine, self.engine.layout
         self.step_count += 1
         b1, b2 = self.betas

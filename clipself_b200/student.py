@@ -220,6 +220,11 @@ class StudentEngine:
         # eva_vit_model.py:500-516): no gradient, no all-reduce, no optimizer update for them
         self.first_trainable = 0
         self.weights_epoch = 0          # bumped by FusedAdamW.step(): in-place updates through the C ABI are invisible to torch
+        # overlapped gradient exchange (opt-in, see allreduce_async): the all-reduce and the fused AdamW run on this side
+        # stream while the main stream already runs the NEXT step's frozen teacher
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+        self.grads_ready: Optional[torch.cuda.Event] = None      # recorded on comm_stream after the all-reduce
+        self.weights_ready: Optional[torch.cuda.Event] = None    # recorded on comm_stream after the fused AdamW
         self.repack()
 
     # ------------------------------------------------------------------ packing
@@ -277,8 +282,34 @@ class StudentEngine:
         o = self.layout.offset[f"blocks.{i}.{first}"]
         return flat[o:o + rows * cols].view(rows, cols)
 
+    # ------------------------------------------------------------------ overlapped gradient exchange
+    def allreduce_async(self) -> None:
+        """The step's ONE collective, issued on a side stream right after the last wgrad: the mean all-reduce (NCCL over
+        NVLink / NVSwitch) of the flat gradient no longer sits at the end of the main stream's critical path.  Consumers
+        order themselves after `grads_ready` (FusedAdamW.step runs on the same side stream; anything that reads the
+        gradients on another stream calls wait_gradients())."""
+        cur = torch.cuda.current_stream()
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.comm_stream.wait_stream(cur)                       # the backward has written every gradient
+        with torch.cuda.stream(self.comm_stream):
+            allreduce_flat_gradient(self.flat_grad, self.layout, self.first_trainable)
+            self.grads_ready = self.comm_stream.record_event()
+
+    def wait_gradients(self) -> None:
+        if self.grads_ready is not None:
+            torch.cuda.current_stream().wait_event(self.grads_ready)
+
+    def wait_weights(self) -> None:
+        """Order the current stream after a fused optimizer step that ran on the side stream."""
+        if self.weights_ready is not None:
+            torch.cuda.current_stream().wait_event(self.weights_ready)
+            self.weights_ready = None
+            self.grads_ready = None
+
     def repack(self) -> None:
         """f32 master -> bf16 GEMM operands (W and W^T), after every optimizer step."""
+        self.wait_weights()
         cfg = self.cfg
         D, Hd = cfg.width, cfg.hidden
         for i, pk in enumerate(self.packs):

@@ -303,7 +303,7 @@ class Workspace:
         self.att = torch.empty(rows, D, **bf)
         self.h = torch.empty(rows, Hd, **bf)
         self.h2 = torch.zeros(rows, Hd, **bf)           # padded columns must stay finite (they meet zero weights)
-        self.stats_att = torch.empty(rows, 2 * cfg.heads, 2, device=device, dtype=torch.float32)
+        self.stats_att = torch.empty(rows, 4 * cfg.heads, 2, device=device, dtype=torch.float32)
         self.stats_h = torch.empty(rows, Hd // 64, 2, device=device, dtype=torch.float32)
         # bf16 copy of the residual stream + its row statistics (written by the proj / w3 / embed epilogues)
         self.xb = torch.empty(rows, D, **bf)
@@ -419,7 +419,7 @@ class TowerEngine:
                          tokens=N, rope_cols=2 * D, ln_fold=(sx[0], pb.c1_qkv, *sx[1:]))
                 ops.attention_fwd(ws.qkv, B, N, cfg.heads, self.scale, ws.att, row_stats=ws.stats_att)
                 ops.gemm(ws.att, pb.wproj_f, x, M=M, bias=pb.c2_proj, residual=x, out2=ws.xb, stats_out=ws.stats_x,
-                         ln_fold=(ws.stats_att, pb.c1_proj, 2 * cfg.heads, D, eps))
+                         ln_fold=(ws.stats_att, pb.c1_proj, 4 * cfg.heads, D, eps))
             else:       # forward_without_attn (eva_vit_model.py:317-324, 249-256): v-projection only, explicit inner LN
                 ops.gemm(ws.xb, pb.wqkv_f[2 * D:], ws.att, M=M, bias=pb.c2_qkv[2 * D:], ln_fold=(sx[0], pb.c1_qkv[2 * D:], *sx[1:]))
                 ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, eps, u)
@@ -438,7 +438,7 @@ class TowerEngine:
             ops.gemm(u, pb.wv, ws.att, M=M, bias=pb.bv)
         if fold_proj:      # inner_attn_ln folded into the proj GEMM's epilogue
             ops.gemm(ws.att, pb.wproj_f, x, M=M, bias=pb.c2_proj, residual=x,
-                     ln_fold=(ws.stats_att, pb.c1_proj, 2 * cfg.heads, D, eps))
+                     ln_fold=(ws.stats_att, pb.c1_proj, 4 * cfg.heads, D, eps))
         else:
             ops.layernorm_fwd(ws.att, M, D, pb.gi, pb.bi, eps, u)
             ops.gemm(u, pb.wproj, x, M=M, bias=pb.bproj, residual=x)

@@ -151,17 +151,26 @@ class CLIPSelf:
             if tar_size != cur_h:
                 images = ops.resize_bilinear(images.contiguous(), tar_size)
 
-        # student forward first: it only needs the (small) images, so it overlaps the crop H2D stream
         model.visual.sync_gradients = bool(distributed)
+
+        def run_teacher():
+            with torch.no_grad():
+                if crop_events is not None:
+                    feats = dist_model.visual.forward_chunked(crops, crop_events)
+                    self._crops_free.record()
+                    return feats
+                return dist_model.encode_image(crops, normalize=False)
+
+        # Order: normally the student forward goes first (it only needs the small images, so it overlaps the crop H2D
+        # stream).  With the overlapped gradient exchange the frozen teacher goes first: it does not depend on the weights
+        # the previous step's all-reduce + AdamW are still producing on the side stream, the student forward does.
+        teacher_first = bool(distributed) and model.visual.overlap_gradient_sync
+        teacher_crop_features = run_teacher() if teacher_first else None
         student_roi_features = model.visual.roi_features_packed(images, rois, offsets, R)
         if streamed_images:
             self._images_free.record()
-        with torch.no_grad():
-            if crop_events is not None:
-                teacher_crop_features = dist_model.visual.forward_chunked(crops, crop_events)
-                self._crops_free.record()
-            else:
-                teacher_crop_features = dist_model.encode_image(crops, normalize=False)
+        if teacher_crop_features is None:
+            teacher_crop_features = run_teacher()
 
         loss_cosine = cosine_distill_loss(student_roi_features, teacher_crop_features,
                                           float(getattr(args, "cosine_weight", 1.0)))

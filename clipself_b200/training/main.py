@@ -175,6 +175,7 @@ def main(argv=None):
             f"these parameters would silently stay constant: {trainable_outside_blocks[:6]} — pass --lock-image")
     model.train()
     dist_model.eval()
+    model.visual.overlap_gradient_sync = args.distributed         # all-reduce + AdamW under the next step's teacher
     method = CLIPSelf()
 
     # student images at --det-image-size (scripts: 1024 / 896), teacher crops at the tower's own size
@@ -238,6 +239,8 @@ def main(argv=None):
                 for g in optimizer.param_groups:
                     g["lr"] = scheduler(step)
             eng = model.visual._student
+            if args.grad_clip_norm is not None or scaler is not None:
+                eng.wait_gradients()                               # the norm / finiteness checks read the reduced gradient
             span = eng.flat_grad[eng.layout.decay_start(eng.first_trainable):eng.layout.n_grad]
             grad_scale = 1.0 / scaler.scale_value if scaler is not None else 1.0     # scaler.unscale_ (train.py:108)
             finite = scaler.check(span) if scaler is not None else True

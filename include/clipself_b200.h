@@ -234,8 +234,8 @@ int cs_pack_swiglu_weights(const void* w1, const void* w2, cs_dtype_t dtype, int
 /* Non-causal softmax attention over the packed projections (eva_vit_model.py:206-217 / 221-246):
  *   qkv [B*N, 3*D] bf16 (q | k | v, each H heads of 64, RoPE already applied to q,k),
  *   out [B*N, D] bf16;  lse [B,H,N] f32 optional (needed for the backward).  head_dim must be 64.
- *   row_stats (optional, N <= 224 only): [B*N, 2H, 2] f32 partial (sum, sum of squares) of every
- *   output row per (head, 32-dim half) — consumed by the LayerNorm-folded proj GEMM (ln_* fields of
+ *   row_stats (optional): [B*N, 4H, 2] f32 partial (sum, sum of squares) of every
+ *   output row per (head, 16-dim quarter) — consumed by the LayerNorm-folded proj GEMM (ln_* fields of
  *   cs_gemm_epilogue_t) so inner_attn_ln (eva_vit_model.py:218) needs no pass of its own.
  *   N <= 224 runs the tcgen05 kernel (S/O in TMEM), longer sequences the streaming kernel. */
 int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_bf16,

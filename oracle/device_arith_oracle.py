@@ -99,16 +99,17 @@ def _attention_core(ar: Arith, qkv: Tensor, cfg, cos: Tensor, sin: Tensor):
 
 def softmax_pv(ar: Arith, q: Tensor, k: Tensor, v: Tensor, block: int = 128) -> Tensor:
     """softmax(q k^T / sqrt(hd)) v on bf16 q, k, v [..., N, hd] with the kernels' rounding points.
-    N <= 224 (attention_tc.cu): one pass, P = ex2(s*c - max*c) rounded to bf16 for the MMA, row sum from the f32 P.
-    N  > 224 (attention_tc_long.cu): keys stream in blocks of 128 with the online softmax: P of a block is taken relative
+    N <= 208 (attention_tc2.cu): one pass, P = ex2(s*c - max*c) rounded to bf16 for the MMA, and the row sum is taken by the
+    tensor core from the SAME rounded P (P times a block of ones), i.e. the exact normaliser of the P V product.
+    N  > 208 (attention_tc_long.cu): keys stream in blocks of 128 with the online softmax: P of a block is taken relative
     to the RUNNING maximum (so its bf16 rounding differs from the one-pass form), the output and the row sum are rescaled
     by 2^((m_old - m_new) c) in f32."""
     N, hd = q.shape[-2], q.shape[-1]
     c = hd ** -0.5 * LOG2E
     s = q @ k.transpose(-2, -1)                                  # f32 accumulate of bf16 products
-    if N <= 224:
-        p = torch.exp2(s * c - s.amax(-1, keepdim=True) * c)
-        return (ar.r(p) @ v) / p.sum(-1, keepdim=True)
+    if N <= 208:
+        p = ar.r(torch.exp2(s * c - s.amax(-1, keepdim=True) * c))
+        return (p @ v) / p.sum(-1, keepdim=True)
     m_run = torch.full(s.shape[:-1] + (1,), float("-inf"))
     l_run = torch.zeros_like(m_run)
     o_run = torch.zeros(q.shape[:-1] + (v.shape[-1],))

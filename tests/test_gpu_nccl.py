@@ -56,7 +56,25 @@ def _worker(rank, world, port, out):
     identical = all(torch.equal(gathered[0], g) for g in gathered)
     err = ((synced - mean).norm() / mean.norm()).item()
     differ = ((local[0] - local[1]).norm() / local[0].norm()).item()
-    out[rank] = (bool(identical), err, differ)
+    # the overlapped form (side-stream all-reduce + fused AdamW, teacher first): same gradients, and after the optimizer
+    # step the weights are bit-identical on every rank
+    from clipself_b200.optim import FusedAdamW
+    student.visual.overlap_gradient_sync = True
+    synced2 = grads_of(rank, True)
+    eng = student.visual._student
+    eng.wait_gradients()
+    torch.cuda.synchronize()
+    same_as_blocking = torch.equal(synced2[: eng.layout.n_grad], eng.flat_grad[: eng.layout.n_grad]) and torch.equal(synced2, synced)
+    opt = FusedAdamW(eng, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    opt.step()
+    assert eng.weights_ready is not None
+    eng.wait_weights()
+    torch.cuda.synchronize()
+    w = eng.flat_param.clone()
+    ws = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    weights_identical = all(torch.equal(ws[0], x) for x in ws)
+    out[rank] = (bool(identical), err, differ, bool(same_as_blocking), bool(weights_identical))
     dist.destroy_process_group()
 
 
@@ -66,8 +84,9 @@ def test_one_step_gradients_identical_across_ranks_and_equal_the_mean():
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(world, 29500 + os.getpid() % 2000, out), nprocs=world, join=True)
     for rank in range(world):
-        identical, err, differ = out[rank]
+        identical, err, differ, same_as_blocking, weights_identical = out[rank]
         print(f"rank {rank}: identical across ranks {identical}, |synced - mean| / |mean| = {err:.2e}, shards differ by {differ:.2f}")
         assert identical
         assert err <= 1e-6            # NCCL AVG over 2 ranks in f32 vs torch mean: rounding of one add + one scale
         assert differ > 1e-2          # the two shards really had different gradients
+        assert same_as_blocking and weights_identical

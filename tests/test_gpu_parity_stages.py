@@ -105,12 +105,12 @@ def test_frozen_tower_stages(which, blocks):
             o = _attention_ref(dq, n, N, H)
             da = ws.att[:M].cpu().float().view(n, N, D)
             check("attention", da, bf(o), TOL_BF16)
-            st = ws.stats_att[:M].cpu().view(n, N, 2 * H, 2).sum(2)
+            st = ws.stats_att[:M].cpu().view(n, N, 4 * H, 2).sum(2)
             check("stats_att", st[..., 1], (o * o).sum(-1), 2e-5)
             # ---- proj with inner_attn_ln folded, residual add, new stream emitted as f32 + bf16 + statistics
             xin = ws.x[:M].cpu().clone().view(n, N, D)
             ops.gemm(ws.att, pb.wproj_f, ws.x, M=M, bias=pb.c2_proj, residual=ws.x, out2=ws.xb, stats_out=ws.stats_x,
-                     ln_fold=(ws.stats_att, pb.c1_proj, 2 * H, D, eps))
+                     ln_fold=(ws.stats_att, pb.c1_proj, 4 * H, D, eps))
             Wf = bf(sd[p + "attn.proj.weight"] * sd[p + "attn.inner_attn_ln.weight"][None, :])
             c2 = sd[p + "attn.proj.weight"] @ sd[p + "attn.inner_attn_ln.bias"] + sd[p + "attn.proj.bias"]
             mean, rstd = _moments(st, D)

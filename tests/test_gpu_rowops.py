@@ -75,14 +75,14 @@ def test_attention_fwd(dev, B, N, H):
     print(f"attention B={B} N={N} H={H}: max err {err:.4e}")
     assert err < 2e-2
     torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=1e-3)
-    if N <= 224:
-        stats = torch.full((B * N, 2 * H, 2), float("nan"), device=dev)
+    if True:
+        stats = torch.full((B * N, 4 * H, 2), float("nan"), device=dev)
         out2 = torch.empty_like(out)
         ops.attention_fwd(qkv, B, N, H, 0.125, out2, None, stats)
         assert torch.equal(out2, out)
         # the statistics are taken from the f32 accumulators before the bf16 rounding of the output:
         # compare with the f32 reference, tolerance = 32 elements x the kernel's per-element error
-        o = ref.view(B * N, 2 * H, 32)
+        o = ref.view(B * N, 4 * H, 16)
         torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-2, atol=5e-2)
         torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-2, atol=5e-2)
 
@@ -113,7 +113,7 @@ def test_attention_fwd_long_tc(dev, B, N, H, monkeypatch):
     qkv = torch.randn(B * N, 3 * D, device=dev).to(torch.bfloat16)
     out = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, H, N, device=dev)
-    stats = torch.full((B * N, 2 * H, 2), float("nan"), device=dev)
+    stats = torch.full((B * N, 4 * H, 2), float("nan"), device=dev)
     ops.attention_fwd(qkv, B, N, H, 0.125, out, lse, stats)
     torch.cuda.synchronize()
     q, k, v = (t.reshape(B, N, H, 64).permute(0, 2, 1, 3) for t in qkv.float().view(B, N, 3, D).unbind(2))
@@ -123,6 +123,6 @@ def test_attention_fwd_long_tc(dev, B, N, H, monkeypatch):
     print(f"long tc attention B={B} N={N} H={H}: max err {err:.4e}")
     assert err < 2e-2
     torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=1e-3)
-    o = ref.view(B * N, 2 * H, 32)
+    o = ref.view(B * N, 4 * H, 16)
     torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-2, atol=5e-2)
     torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-2, atol=5e-2)

@@ -55,12 +55,12 @@ with torch.no_grad():
         pp = torch.exp2(s * sl2 - s.amax(-1, keepdim=True) * sl2)
         o = ((bf(pp) @ dqkv[2]) / pp.sum(-1, keepdim=True)).transpose(1, 2).reshape(n, N, D)
         da = ws.att[:M].cpu().float().view(n, N, D)
-        st = ws.stats_att[:M].cpu().view(n, N, 2 * H, 2).sum(2)
+        st = ws.stats_att[:M].cpu().view(n, N, 4 * H, 2).sum(2)
         print(f"   att  vs bf16(ref) {rel(da, bf(o)):.3e}   flips {(da != bf(o)).float().mean().item():.4f}   stats s1 {rel(st[..., 0], o.sum(-1)):.2e} s2 {rel(st[..., 1], (o * o).sum(-1)):.2e}")
         # --- proj from the DEVICE att + stats
         xin = ws.x[:M].clone()
         ops.gemm(ws.att, pb.wproj_f, ws.x, M=M, bias=pb.c2_proj, residual=ws.x, out2=ws.xb, stats_out=ws.stats_x,
-                 ln_fold=(ws.stats_att, pb.c1_proj, 2 * H, D, eps))
+                 ln_fold=(ws.stats_att, pb.c1_proj, 4 * H, D, eps))
         Wf = bf(sd[p + "attn.proj.weight"] * sd[p + "attn.inner_attn_ln.weight"][None, :])
         c1 = Wf.sum(1); c2 = sd[p + "attn.proj.weight"] @ sd[p + "attn.inner_attn_ln.bias"] + sd[p + "attn.proj.bias"]
         mean = st[..., 0:1] / D; var = (st[..., 1:2] / D - mean * mean).clamp_min(0); rstd = torch.rsqrt(var + eps)
