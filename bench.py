@@ -367,25 +367,86 @@ def pick_threads(fn):
     return best_n, seen
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _load_reference():
+    """The UNMODIFIED reference (pip-installed from /root/reference into baseline/_ref, git-ignored, travels with gpurun):
+    its open_clip package and its CLIPSelf plug-in, behind the import shims for the absent ftfy / timm
+    (oracle/ref_stubs).  Returns None when the install is not there (then the oracle port is timed instead)."""
+    if not os.path.isdir(os.path.join(REF_DIR, "open_clip")):
+        return None
+    saved = list(sys.path)
+    sys.path[:0] = [REF_DIR, os.path.join(ROOT, "oracle", "ref_stubs")]
+    try:
+        for k in [k for k in sys.modules if k == "open_clip" or k.startswith("open_clip.") or k == "training" or k.startswith("training.")]:
+            del sys.modules[k]
+        import io
+        import contextlib
+        with contextlib.redirect_stdout(io.StringIO()):          # "Please 'pip install xformers'" banners
+            import open_clip
+            from training.clipself import CLIPSelf
+        if not os.path.abspath(open_clip.__file__).startswith(REF_DIR):
+            return None
+        return open_clip, CLIPSelf
+    except Exception as e:                                        # noqa: BLE001
+        print(f"bench: reference install in baseline/_ref is unusable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+    finally:
+        sys.path[:] = saved
+
+
+def _reference_models(open_clip, name, seed):
+    """Two reference CustomCLIP models (student, teacher) with the seeded synthetic weights of the oracle, math-attention
+    branch (xformers is absent: eva_vit_model.py:221-246), student locked like the scripts do."""
+    import io
+    import contextlib
+    from oracle import clipself_oracle as O
+    ocfg = O.CFG_B16 if "B-16" in name else O.CFG_L14_336
+    models = []
+    for s in (seed, seed + 1):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = open_clip.create_model(name, "eva", device="cpu", precision="fp32", cache_dir=None)
+        for blk in m.visual.blocks:
+            blk.attn.xattn = False
+        m.visual.load_state_dict(O.synth_tower_weights(ocfg, s), strict=False)
+        models.append(m)
+    models[0].lock_image_tower(unlocked_groups=ocfg.layers)
+    models[0].train()
+    models[1].eval()
+    return ocfg, models[0], models[1]
+
+
 def cpu_baseline(cfg_name, budget_s):
     """Oracle port on the host cores, BASELINE.json configs[0] shape (2 images x 8 boxes, fwd+loss)."""
     from oracle import clipself_oracle as O
     ocfg = O.CFG_B16
-    ssd, tsd = O.synth_tower_weights(ocfg, 1), O.synth_tower_weights(ocfg, 2)
     batch = O.synth_batch(ocfg, 2, 8, 3, kind="grid")
+    ref = _load_reference()
+    if ref is not None:
+        open_clip, RefCLIPSelf = ref
+        _, student, teacher = _reference_models(open_clip, "EVA02-CLIP-B-16", 1)
+        rargs = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+        method = RefCLIPSelf()
+        one = lambda: float(method(batch, student, teacher, None, "cpu", None, False, rargs)[0]["loss_cosine"])   # noqa: E731
+        kind, what = "reference", "the reference's own CLIPSelf.__call__ + open_clip EVA02-CLIP-B-16 (baseline/_ref, torch fp32 CPU)"
+    else:
+        ssd, tsd = O.synth_tower_weights(ocfg, 1), O.synth_tower_weights(ocfg, 2)
+        one = lambda: _oracle_step(O, ocfg, ssd, tsd, batch, False)   # noqa: E731
+        kind, what = "port", "oracle port (torch fp32 CPU), EVA02-B/16"
     with torch.no_grad():
-        threads, sweep = pick_threads(lambda: _oracle_step(O, ocfg, ssd, tsd, batch, False))
+        threads, sweep = pick_threads(one)
         times = []
         t_end = time.perf_counter() + budget_s
         while len(times) < 2 or (time.perf_counter() < t_end and len(times) < 10):
             t0 = time.perf_counter()
-            _oracle_step(O, ocfg, ssd, tsd, batch, False)
+            one()
             times.append(time.perf_counter() - t0)
             if len(times) >= 2 and time.perf_counter() > t_end:
                 break
     best = min(times)
-    return {"value": round(2 / best, 3), "unit": "images/sec", "cores": threads, "kind": "port",
-            "sample": f"oracle port (torch fp32 CPU), EVA02-B/16, 2 images x 8 boxes, forward+loss, min of {len(times)} reps, "
+    return {"value": round(2 / best, 3), "unit": "images/sec", "cores": threads, "kind": kind,
+            "sample": f"{what}, BASELINE configs[0]: 2 images x 8 boxes, forward+loss, min of {len(times)} reps, "
                       f"{threads} threads (thread sweep, s per call: {sweep})"}
 
 
@@ -398,25 +459,41 @@ def run_reference(args):
     from oracle import clipself_oracle as O
     wl = WORKLOADS[args.workload]
     K = wl["boxes"]
-    ocfg = O.CFG_B16
-    ssd, tsd = O.synth_tower_weights(ocfg, 1), O.synth_tower_weights(ocfg, 2)
-    for k, v in ssd.items():
-        if k.startswith("blocks."):
-            v.requires_grad_(True)
-    batch = O.synth_batch(ocfg, 1, K, 3, kind=wl["kind"])
+    ocfg = O.CFG_B16 if "B-16" in wl["model"] else O.CFG_L14_336
+    batch = O.synth_batch(ocfg, 1, K, 3, kind=wl["kind"], det_size=wl.get("det"))
+    ref = _load_reference()
+    if ref is not None:
+        open_clip, RefCLIPSelf = ref
+        _, student, teacher = _reference_models(open_clip, wl["model"], 1)
+        rargs = types.SimpleNamespace(multiscale=False, extract_type="v2", cosine_weight=1.0)
+        method = RefCLIPSelf()
+
+        def one_step():                  # the reference's step: forward through its plug-in, backward (train.py:91-96)
+            for p in student.parameters():
+                p.grad = None
+            losses, _, _ = method(batch, student, teacher, None, "cpu", None, False, rargs)
+            sum(losses.values()).backward()
+        kind, what = "reference", "UNMODIFIED reference (baseline/_ref: training.clipself.CLIPSelf + open_clip " + wl["model"] + ", math attention, torch fp32 CPU"
+    else:
+        ssd, tsd = O.synth_tower_weights(ocfg, 1), O.synth_tower_weights(ocfg, 2)
+        for k, v in ssd.items():
+            if k.startswith("blocks."):
+                v.requires_grad_(True)
+        one_step = lambda: _oracle_step(O, ocfg, ssd, tsd, batch, True)   # noqa: E731
+        kind, what = "port", "oracle port (torch fp32 CPU"
     warm = min(args.warmup, 1) if args.warmup else 0
-    threads, sweep = pick_threads(lambda: _oracle_step(O, ocfg, ssd, tsd, batch, True))    # doubles as the warm-up
+    threads, sweep = pick_threads(one_step)    # doubles as the warm-up
     t0 = time.perf_counter()
     steps = 0
     for _ in range(args.steps):
-        _oracle_step(O, ocfg, ssd, tsd, batch, True)
+        one_step()
         steps += 1
         if time.perf_counter() - t0 > 150:          # keep the whole run within a few minutes
             break
     dt = (time.perf_counter() - t0) / steps
     value = 1.0 / dt
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    sample = (f"oracle port (torch fp32 CPU, {threads} threads): 1 image x {K} boxes per step, "
+    sample = (f"{what}, {threads} threads): 1 image x {K} boxes per step, "
               f"teacher fwd + student fwd+bwd, {steps} steps timed; thread sweep (s per step): {sweep}")
     out = {"impl": "reference", "metric": "images/sec (32 boxes/img) ViT-B/16@224 distill step", "value": round(value, 4),
            "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": max(warm, 1),
@@ -424,7 +501,7 @@ def run_reference(args):
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {wl['model']} bounded CPU sample", "global_batch": 1,
                       "boxes_per_image": K, "parallelism": "cpu"},
-           "cpu_baseline": {"value": round(value, 4), "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": round(value, 4), "unit": "images/sec", "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 4), "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -91,7 +91,30 @@ col_partials_kernel(const TDY* __restrict__ dy, long long lddy, const TX* __rest
     const long long r0 = s * rows_per, r1 = min(M, r0 + rows_per);
     float dg = 0.f, db = 0.f;
     if (c < D) {
-        for (long long m = r0; m < r1; ++m) {
+        long long m = r0;
+        // 8 rows per trip with every load issued before the first use: the loop is latency bound otherwise (one dependent
+        // global load per row and thread); the summation order stays row-ascending, i.e. deterministic
+        for (; m + 8 <= r1; m += 8) {
+            float g[8], xv[8], mu[8], rs[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = (float)dy[(m + u) * lddy + c];
+            if (x != nullptr) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long mm = m + u;
+                    const long long prow = mm * row_mul + (row_div > 0 ? mm / row_div : 0) + row_off;
+                    xv[u] = (float)x[prow * ldx + c];
+                    mu[u] = mean[mm];
+                    rs[u] = rstd[mm];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                db += g[u];
+                if (x != nullptr) dg += g[u] * (xv[u] - mu[u]) * rs[u];
+            }
+        }
+        for (; m < r1; ++m) {
             const float g = (float)dy[m * lddy + c];
             db += g;
             if (x != nullptr) {
