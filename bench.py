@@ -298,8 +298,10 @@ def run_b200(args):
         pass
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")))
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # per launch, from the committed ncu capture
+        # per launch of the dominant instantiation AT THE STEP'S SHAPE (M = 512 crops x 197 tokens), from the committed
+        # ncu --set full capture (profiles/r02_ncu_dominant_kernels.txt); cfg2 only — null for the other workloads
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant_kernel_traffic.json")))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"] if args.workload in ("cfg2", "cfg3") else None
     except (OSError, KeyError):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)

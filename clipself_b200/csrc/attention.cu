@@ -536,6 +536,8 @@ int attention_fwd_tc3(const void* qkv, int B, int N, int H, float scale, void* o
                       cudaStream_t st);
 int attention_fwd_tc_long(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
                           cudaStream_t st);
+int attention_fwd_tc4(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, float* row_stats,
+                      cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* d_out, const float* lse, const float* delta, int B, int N, int H,
                      float scale, const float* rope_cos, const float* rope_sin, void* dqkv, cudaStream_t st);
 }
@@ -557,6 +559,10 @@ extern "C" int cs_attention_fwd(const void* qkv_bf16, int B, int N, int H, float
         // longer sequences (ViT-L/14-336: 577, the 1024 px student: 4097).  CS_ATTN_LEGACY=1 selects the mma.sync kernel
         // below for A/B measurements; CS_ATTN_FORCE_LONG=1 routes short sequences through the streaming kernel.
         static const bool legacy = env_on("CS_ATTN_LEGACY");
+        if (!legacy && !env_on("CS_ATTN_FORCE_LONG") && !env_on("CS_ATTN_V1") && !env_on("CS_ATTN_V3")) {   // 129 <= N <= 208: two ping-pong slots (attention_tc4.cu)
+            const int rc = attention_fwd_tc4(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
+            if (rc != CS_ERR_UNSUPPORTED) return rc;
+        }
         if (!legacy && !env_on("CS_ATTN_FORCE_LONG") && !env_on("CS_ATTN_V1")) {     // N <= 208: 16-softmax-warp kernel (attention_tc3.cu)
             const int rc = attention_fwd_tc3(qkv_bf16, B, N, H, scale, out_bf16, lse, row_stats, (cudaStream_t)stream);
             if (rc != CS_ERR_UNSUPPORTED) return rc;

@@ -92,6 +92,37 @@ static int encode_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, i
     return CS_OK;
 }
 
+int make_map_bf16_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t n1, int64_t n2, int box_cols, int box_rows) {
+    // same cache as the 2D maps; the key cannot collide with a 2D one (ld < 0 marks the 3D geometry)
+    const MapKey key{ptr, n2, cols, -n1, box_cols, box_rows};
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+        *map = it->second;
+        return CS_OK;
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return CS_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)n1, (cuuint64_t)n2};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * (cuuint64_t)n1};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3D) failed (%d): ptr=%p cols=%lld n1=%lld n2=%lld", (int)r, ptr, (long long)cols,
+                  (long long)n1, (long long)n2);
+        return CS_ERR_CUDA;
+    }
+    if (g_map_cache.size() >= 8192) g_map_cache.clear();
+    g_map_cache.emplace(key, *map);
+    ++g_map_encodes;
+    return CS_OK;
+}
 
 }  // namespace cs
 

@@ -59,7 +59,8 @@ def test_im2col(dev, dtype, S, P):
     assert (out[:, k:] == 0).all()
 
 
-@pytest.mark.parametrize("B,N,H", [(3, 197, 12), (2, 17, 2), (1, 577, 16), (2, 64, 1), (2, 65, 3)])
+@pytest.mark.parametrize("B,N,H", [(3, 197, 12), (2, 17, 2), (1, 577, 16), (2, 64, 1), (2, 65, 3),
+                                   (2, 129, 2), (5, 208, 3), (3, 161, 1), (2, 193, 2), (150, 197, 12)])
 def test_attention_fwd(dev, B, N, H):
     from clipself_b200 import ops
     D = H * 64
