@@ -9,7 +9,8 @@ namespace cs {
 // (cached per (address, geometry, box): no driver call in steady state)
 int make_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                      int box_rows);
-// host: 3D bf16 tensor map over a row-major [n2][n1][cols] tensor (SWIZZLE_128B), box = [1][box_rows][box_cols]: a tile that
+// host: 3D bf16 tensor map over a row-major [n2][n1][cols] tensor, box = [1][box_rows][box_cols] (SWIZZLE_128B / SWIZZLE_64B when the
+// box is 128 / 64 bytes wide, dense otherwise): a tile that
 // crosses n1 is clipped there (used by the attention kernels to store per-image tiles).  Cached like the 2D maps.
 int make_map_bf16_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t n1, int64_t n2, int box_cols, int box_rows);
 long long tensor_map_encode_count();   // driver encodes so far (cache misses) — exported as cs_tensor_map_encodes()

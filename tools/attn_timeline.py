@@ -13,7 +13,7 @@ stats = torch.empty(B * N, 4 * H, 2, device=dev)
 for _ in range(3):
     ops.attention_fwd(qkv, B, N, H, 0.125, out, None, stats)
 torch.cuda.synchronize()
-buf = np.zeros((12, 256), dtype=np.uint64)
+buf = np.zeros((20, 256), dtype=np.uint64)
 L = _lib.lib()
 L.cs_debug_attn_timeline.argtypes = [ctypes.c_void_p]
 assert L.cs_debug_attn_timeline(buf.ctypes.data) == 0
@@ -22,16 +22,16 @@ items = range(int(sys.argv[2]) if len(sys.argv) > 2 else 3, int(sys.argv[3]) if 
 t0 = t[0, 6 * items[0]]
 ev = []
 names = ["S ready", "max done", "exp done", "O ready", "O read", "epi done"]
-for w, tag in ((0, "slot0"), (4, "slot1")):
+for w, tag in ((0, "slot0"), (8, "slot1")):
     for i in items:
         for k in range(6):
             ev.append((t[w, 6 * i + k] - t0, f"{tag} item {i}: {names[k]}"))
 mn = ["S0 wait", "S0 issue", "S1 wait", "S1 issue", "PV0 wait", "PV0 issue", "PV1 wait", "PV1 issue"]
 for i in items:
     for k in range(8):
-        ev.append((t[9, 8 * i + k] - t0, f"  mma  item {i}: {mn[k]}"))
+        ev.append((t[17, 8 * i + k] - t0, f"  mma  item {i}: {mn[k]}"))
     for k, n in enumerate(["K", "Q0", "Q1", "V"]):
-        ev.append((t[8, 4 * i + k] - t0, f"    tma item {i}: {n} issued"))
+        ev.append((t[16, 4 * i + k] - t0, f"    tma item {i}: {n} issued"))
 for c, s in sorted(ev):
     print(f"{c:8d}  {s}")
 per = (t[0, 6 * items[-1]] - t[0, 6 * items[0]]) / (len(items) - 1)
