@@ -29,9 +29,12 @@ constexpr int ROPE_STRIDE = 65;                    // [16 freqs][64 grid positio
 // CG = 2: a CTA pair (cluster of 2 on one TPC) per 256 x BLOCK_N tile: UMMA M = 256, each CTA owns 128 rows of the
 //         accumulator in its own TMEM and stages only HALF of the B tile (the tensor cores of the pair share it), so the
 //         operand bytes a CTA pulls from L2 per flop drop by a third and 6 instead of 4 stages fit.
-template <int BLOCK_N, int CG = 1>
+// EMIT (new residual stream as f32 + bf16 + statistics): the outputs leave through double-buffered staging tiles and
+//         cp.async.bulk.tensor stores (direct stores stalled the epilogue warps: 243 -> 143 us without them), paid for with
+//         one mainloop stage.
+template <int BLOCK_N, int CG = 1, bool EMIT = false>
 struct Cfg {
-    static constexpr int STAGES = (BLOCK_N == 256 && CG == 1) ? 4 : 6;
+    static constexpr int STAGES = (BLOCK_N == 256 && CG == 1) ? (EMIT ? 3 : 4) : (EMIT ? 5 : 6);
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_ROWS = BLOCK_N / CG;               // rows of W staged by one CTA
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
@@ -39,7 +42,8 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two)
     static constexpr int HALF_N = BLOCK_N / 2;     // accumulator columns owned by one epilogue warp
     static constexpr int BAR_BYTES = 256;
-    static constexpr int EPI_TILE_BYTES = 32 * 64;           // one swizzled 32-row x 64 B staging tile per warp
+    static constexpr int EPI_TILE_BYTES = EMIT ? 2 * (32 * 64 + 32 * 32) : 32 * 64;   // one swizzled 32-row x 64 B staging tile per warp
+                                                             // (EMIT: two f32 tiles, then two 32-row x 32 B bf16 tiles)
     static constexpr int EPI_VEC_BYTES = HALF_N * 4;         // this warp's bias slice / ln_c1 slice
     static constexpr int EPI_WARP_BYTES = EPI_TILE_BYTES + 2 * EPI_VEC_BYTES;
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
@@ -86,7 +90,8 @@ enum ResKind { RES_NONE = 0, RES_LOAD = 1, RES_RED = 2 };
 template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t taddr, int mw, int n0, int half, int M, int N,
                                               uint8_t* st, float* sbias, const float* srope, int lane, bool use_bias,
-                                              uint32_t tfull, uint32_t tfull_phase) {
+                                              uint32_t tfull, uint32_t tfull_phase, const CUtensorMap* map_o32,
+                                              const CUtensorMap* map_o16) {
     using C = Cfg<BLOCK_N>;
     constexpr int HALF_N = C::HALF_N;
     constexpr bool SWI = (MODE == CS_EPI_SWIGLU);
@@ -214,6 +219,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                 if (acc == 1.2345e-30f) *reinterpret_cast<float*>(ep.out) = acc;
                 continue;
             }
+            // the staging tile (32 rows x 64 B, SWIZZLE_64B pattern) leaves as ONE bulk tensor store: rows beyond M are clipped
+            // by the map, no read-back and no per-thread global stores (they cost ~10 % of the kernel).  The previous
+            // round's store must have read the tile before it is rewritten.
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 pk;
@@ -223,16 +233,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                 pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
                 *reinterpret_cast<uint4*>(st + lane * 64 + ((j ^ swz) << 4)) = pk;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(ep.out) + out_n0 + r + cch * 8;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rr = i * 8 + crow;
-                const uint4 val = *reinterpret_cast<const uint4*>(st + rr * 64 + ((cch ^ ((rr >> 1) & 3)) << 4));
-                if (mw + rr < M && !(ep.dbg & 1))      // ablation bit 0: no global stores
-                    *reinterpret_cast<uint4*>(obase + (long long)(mw + rr) * ep.ldo) = val;
+            if (lane == 0 && !(ep.dbg & 1)) {      // ablation bit 0: no global stores
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_o16),
+                             "r"(smem_u32(st)), "r"(out_n0 + r), "r"(mw)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            __syncwarp();
         }
         if constexpr (SWI) {
             if (ep.stats_out != nullptr && m < M)
@@ -275,11 +283,22 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
         }
         wait_accumulator();
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};      // EMIT: statistics of this lane's 4 rows
+        const uint32_t st_s = smem_u32(st);
 #pragma unroll
         for (int rd = 0; rd < ROUNDS; ++rd) {
             const int r = rd * 16;
             const int nc = nbase + r;
             const bool col_ok = n0 + half * HALF_N + r < N;          // warp-uniform (N % 32 == 0)
+            // EMIT: staging buffer rd & 1 (f32 tile at 2048 * b, bf16 tile at 4096 + 1024 * b); the bulk stores of round
+            // rd - 2 must have read it
+            uint8_t* stf = EMIT ? st + (rd & 1) * 2048 : st;
+            uint8_t* sth = st + 4096 + (rd & 1) * 1024;
+            if constexpr (EMIT) {
+                if (rd >= 2) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+            }
             float4 ex[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) ex[i] = HAS_EXTRA ? extra[rd % PF][i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -294,15 +313,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                 for (int j = 0; j < 4; ++j) {
                     float4 f;
                     if constexpr (LNFOLD) {
-                        f.x = fmaf(rs, __uint_as_float(a[4 * j]), -rm * sc1[r + 4 * j]);
-                        f.y = fmaf(rs, __uint_as_float(a[4 * j + 1]), -rm * sc1[r + 4 * j + 1]);
-                        f.z = fmaf(rs, __uint_as_float(a[4 * j + 2]), -rm * sc1[r + 4 * j + 2]);
-                        f.w = fmaf(rs, __uint_as_float(a[4 * j + 3]), -rm * sc1[r + 4 * j + 3]);
+                        const float4 c4 = *reinterpret_cast<const float4*>(sc1 + r + 4 * j);     // one 16-byte broadcast read
+                        f.x = fmaf(rs, __uint_as_float(a[4 * j]), -rm * c4.x);
+                        f.y = fmaf(rs, __uint_as_float(a[4 * j + 1]), -rm * c4.y);
+                        f.z = fmaf(rs, __uint_as_float(a[4 * j + 2]), -rm * c4.z);
+                        f.w = fmaf(rs, __uint_as_float(a[4 * j + 3]), -rm * c4.w);
                     } else {
                         f = make_float4(__uint_as_float(a[4 * j]) * ep.alpha, __uint_as_float(a[4 * j + 1]) * ep.alpha,
                                         __uint_as_float(a[4 * j + 2]) * ep.alpha, __uint_as_float(a[4 * j + 3]) * ep.alpha);
                     }
-                    *reinterpret_cast<float4*>(st + lane * 64 + ((j ^ swz) << 4)) = f;
+                    *reinterpret_cast<float4*>(stf + lane * 64 + ((j ^ swz) << 4)) = f;
                 }
             }
             __syncwarp();
@@ -311,12 +331,25 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int rr = i * 8 + crow;
-                    float4 f = *reinterpret_cast<const float4*>(st + rr * 64 + ((cch ^ ((rr >> 1) & 3)) << 4));
+                    float4* slot = reinterpret_cast<float4*>(stf + rr * 64 + ((cch ^ ((rr >> 1) & 3)) << 4));
+                    float4 f = *slot;
                     f.x += b4.x + ex[i].x;
                     f.y += b4.y + ex[i].y;
                     f.z += b4.z + ex[i].z;
                     f.w += b4.w + ex[i].w;
-                    if (orow[i] >= 0 && !(ep.dbg & 1)) {
+                    if constexpr (EMIT) {
+                        // final values back into the (SWIZZLE_64B) f32 tile, their bf16 copy into the dense 32-byte-row tile;
+                        // rows beyond M are clipped by the store maps
+                        *slot = f;
+                        uint2 pk;
+                        pk.x = pack_bf16(f.x, f.y);
+                        pk.y = pack_bf16(f.z, f.w);
+                        *reinterpret_cast<uint2*>(sth + rr * 32 + cch * 8) = pk;
+                        if (orow[i] >= 0) {
+                            s1[i] += (f.x + f.y) + (f.z + f.w);
+                            s2[i] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, s2[i]))));
+                        }
+                    } else if (orow[i] >= 0 && !(ep.dbg & 1)) {
                         float* dst = reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + nc;
                         if constexpr (RES == RES_RED) {
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w)
@@ -324,17 +357,28 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
                         } else {
                             *reinterpret_cast<float4*>(dst) = f;
                         }
-                        if constexpr (EMIT) {
-                            uint2 pk;
-                            pk.x = pack_bf16(f.x, f.y);
-                            pk.y = pack_bf16(f.z, f.w);
-                            *reinterpret_cast<uint2*>(ep.out2 + orow[i] * ep.ldo2 + nc) = pk;
-                            s1[i] += (f.x + f.y) + (f.z + f.w);
-                            s2[i] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, s2[i]))));
-                        }
                     }
                 }
             }
+            if constexpr (EMIT) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // staging writes -> visible to the bulk stores
+                __syncwarp();
+                if (lane == 0 && col_ok && !(ep.dbg & 1)) {
+                    const int c0 = n0 + half * HALF_N + r;
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_o32),
+                                 "r"(st_s + (uint32_t)((rd & 1) * 2048)), "r"(c0), "r"(mw)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map_o16),
+                                 "r"(st_s + (uint32_t)(4096 + (rd & 1) * 1024)), "r"(c0), "r"(mw)
+                                 : "memory");
+                }
+                if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            } else {
+                __syncwarp();
+            }
+        }
+        if constexpr (EMIT) {       // the staging tiles are rewritten by the next tile's first rounds
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
         }
         if constexpr (EMIT) {
@@ -356,8 +400,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
 template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_o16,
             int M, int N, int K, const EpiParams ep) {
-    using C = Cfg<BLOCK_N, CG>;
+    using C = Cfg<BLOCK_N, CG, EMIT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
@@ -391,6 +436,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if constexpr (EMIT) tma_prefetch_desc(&map_o32);
+        if constexpr (EMIT || OUT_BF16) tma_prefetch_desc(&map_o16);
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -517,11 +564,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             epilogue_tile<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT>(ep, taddr, m0 + quarter * 32, n0, half, M, N, st, sbias,
-                                                                      srope, lane, tile < num_mn, tfull_bar(acc), acc_phase);
+                                                                      srope, lane, tile < num_mn, tfull_bar(acc), acc_phase, &map_o32, &map_o16);
             tc_fence_before();
             if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);
             else mbar_arrive(tempty_bar(acc));
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // staged tiles are read before the CTA retires
     }
 
     tc_fence_before();
@@ -548,7 +596,20 @@ static bool use_cta_pairs() {
 template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG>
 static int launch_cg(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t stream) {
-    using C = Cfg<BLOCK_N, CG>;
+    using C = Cfg<BLOCK_N, CG, EMIT>;
+    // EMIT: store maps of the two outputs, one 32-row x 16-column box per epilogue round (f32: 64-byte rows in the
+    // SWIZZLE_64B pattern of the staging tile, bf16: dense 32-byte rows); cached like the operand maps
+    CUtensorMap mo32 = ma, mo16 = ma;
+    if constexpr (EMIT) {
+        int rc = make_map_2d(&mo32, ep.out, 4, M, N, ep.ldo, 16, 32, 64);
+        if (rc) return rc;
+        rc = make_map_2d(&mo16, ep.out2, 2, M, N, ep.ldo2, 16, 32, 0);
+        if (rc) return rc;
+    }
+    if constexpr (OUT_BF16) {   // bf16 outputs: one 32-row x 32-column box (64-byte rows, SWIZZLE_64B) per epilogue round
+        const int rc = make_map_2d(&mo16, ep.out, 2, M, MODE == CS_EPI_SWIGLU ? N / 2 : N, ep.ldo, 32, 32, 64);
+        if (rc) return rc;
+    }
     auto kern = gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, CG>;
     static bool configured = false;
     if (!configured) {
@@ -570,7 +631,7 @@ static int launch_cg(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
+    CS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo32, mo16, M, N, K, ep));
     return CS_OK;
 }
 
@@ -703,8 +764,8 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                          e->mode != CS_EPI_TOKENS && ((uintptr_t)e->ln_stats % 16 == 0) && ((uintptr_t)e->ln_c1 % 16 == 0),
                      "cs_gemm_bf16: LN folding needs ln_c1, even ln_parts, ln_dim, alpha == 1 (any mode but TOKENS)");
     if (e->out2_bf16)
-        CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual && ((uintptr_t)e->out2_bf16 % 8 == 0) &&
-                         e->ldo2 % 4 == 0,
+        CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual && ((uintptr_t)e->out2_bf16 % 16 == 0) &&
+                         e->ldo2 % 8 == 0,
                      "cs_gemm_bf16: out2_bf16 (bf16 copy + row statistics of the new residual stream) needs the f32 STORE "
                      "epilogue with a residual");
     if (e->stats_out) CS_CHECK_ARG(e->mode == CS_EPI_SWIGLU || e->out2_bf16, "cs_gemm_bf16: stats_out is a SWIGLU / out2_bf16 output");

@@ -92,6 +92,41 @@ static int encode_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, i
     return CS_OK;
 }
 
+int make_map_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                int box_rows, int swizzle_bytes) {
+    // the key cannot collide with the bf16 SWIZZLE_128B maps: box_cols carries the element size and swizzle in its high bits
+    const MapKey key{ptr, rows, cols, ld, box_cols | (elem_bytes << 16) | (swizzle_bytes << 20) | (1 << 30), box_rows};
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+        *map = it->second;
+        return CS_OK;
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return CS_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (2D, %d-byte elements) failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld", elem_bytes, (int)r,
+                  ptr, (long long)rows, (long long)cols, (long long)ld);
+        return CS_ERR_CUDA;
+    }
+    if (g_map_cache.size() >= 8192) g_map_cache.clear();
+    g_map_cache.emplace(key, *map);
+    ++g_map_encodes;
+    return CS_OK;
+}
+
 int make_map_bf16_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t n1, int64_t n2, int box_cols, int box_rows) {
     // same cache as the 2D maps; the key cannot collide with a 2D one (ld < 0 marks the 3D geometry)
     const MapKey key{ptr, n2, cols, -n1, box_cols, box_rows};

@@ -9,6 +9,9 @@ namespace cs {
 // (cached per (address, geometry, box): no driver call in steady state)
 int make_map_bf16_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                      int box_rows);
+// host: generic 2D tensor map, elem_bytes 2 (bf16) or 4 (f32), swizzle_bytes 0 / 32 / 64 / 128; cached like the others
+int make_map_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                int box_rows, int swizzle_bytes);
 // host: 3D bf16 tensor map over a row-major [n2][n1][cols] tensor, box = [1][box_rows][box_cols] (SWIZZLE_128B / SWIZZLE_64B when the
 // box is 128 / 64 bytes wide, dense otherwise): a tile that
 // crosses n1 is clipped there (used by the attention kernels to store per-image tiles).  Cached like the 2D maps.

@@ -6,7 +6,7 @@ from clipself_b200 import ops, _lib as L
 from clipself_b200.tower import rope_vectors
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-M = 128 * 197
+M = int(os.environ.get("M_CROPS", "128")) * 197
 
 
 def run(name, N, K, mode, odt, res, dbg, fold=False, emit=False):
@@ -43,6 +43,11 @@ import sys as _s
 if len(_s.argv) > 1 and _s.argv[1] == "bits":
     for dbg in (0, 1, 2, 4, 5, 6, 8):
         run("w12 store bf16 N=4096", 4096, 768, L.EPI_STORE, torch.bfloat16, 0, dbg)
+    _s.exit(0)
+if len(_s.argv) > 1 and _s.argv[1] == "emit":
+    for dbg in (0, 16, 1, 8):          # 16: no L2 prefetch of the next tile's residual; 1: no global stores; 8: mainloop only
+        run("proj fold emit N=768", 768, 768, L.EPI_STORE, torch.float32, 0, dbg, fold=True, emit=True)
+        run("w3 fold emit N=768 K=2048", 768, 2048, L.EPI_STORE, torch.float32, 0, dbg, fold=True, emit=True)
     _s.exit(0)
 for dbg in (0, 8):
     run("w12 store bf16 N=4096", 4096, 768, L.EPI_STORE, torch.bfloat16, 0, dbg)
