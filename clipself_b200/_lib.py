@@ -52,6 +52,7 @@ PROTOTYPES = {
     "cs_layernorm_fwd": [vp, i32, i64, i64, i32, i32, i32, i32, vp, vp, f32, vp, i64, vp, vp, vp],
     "cs_row_stats_cast": [vp, i64, i64, i32, vp, i64, vp, i32, vp],
     "cs_gemm_bf16": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],
+    "cs_gemm_bf16_tn": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],
     "cs_pack_swiglu_weights": [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp],
     "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp, vp],
     "cs_cast_pad_bf16": [vp, i64, i64, i64, vp, i64, vp],

@@ -130,8 +130,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid
             mbar_init(r_full(s), 1);
             mbar_init(r_empty(s), 1);
             mbar_init(t_full(s), 1);
-            mbar_init(t_empty(s), 256);
-            mbar_init(e_full(s), 256);
+            mbar_init(t_empty(s), 8);       // one elected arrival per softmax warp
+            mbar_init(e_full(s), 8);
             mbar_init(e_empty(s), 1);
         }
         for (int s = 0; s < STAGES; ++s) {
@@ -139,7 +139,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid
             mbar_init(x_empty(s), 1);
         }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 256);
+        mbar_init(acc_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -274,7 +274,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid
                 tmem_ld32(tmem_base + lane_addr + (uint32_t)(T2_COL + buf * BS + half * 32), dv);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(t_empty(buf));                          // products of block c+2 may overwrite this buffer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(buf));                          // products of block c+2 may overwrite this buffer
                 const float* v_lse = vec + (st * 2 + 0) * BS + half * 32;
                 const float* v_dl = vec + (st * 2 + 1) * BS + half * 32;
                 const int col0 = j * BS + half * 32;                // streamed index of this thread's first column
@@ -308,7 +309,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
                 tc_fence_before();
-                mbar_arrive(e_full(buf));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e_full(buf));
             }
             // ---- gradient tile(s) of this item
             mbar_wait(acc_full, (uint32_t)(il & 1));
@@ -318,7 +320,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid
             if (kDKV) tmem_ld32(tmem_base + lane_addr + (uint32_t)(ACC2_COL + half * 32), a2);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(acc_empty);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
             if (row < p.N) {
                 float g1[32], g2[32];
 #pragma unroll

@@ -92,11 +92,11 @@ attention_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap map, const Para
                 mbar_init(q_empty(s, g), 1);
             }
             mbar_init(s_full(g), 1);
-            mbar_init(s_empty(g), 128);
-            mbar_init(p_full(g), 128);
+            mbar_init(s_empty(g), 4);        // one elected arrival per warp of the group
+            mbar_init(p_full(g), 4);
             mbar_init(p_empty(g), 1);
             mbar_init(o_full(g), 1);
-            mbar_init(o_empty(g), 128);
+            mbar_init(o_empty(g), 4);
         }
         for (int s = 0; s < KV_STAGES; ++s) {
             mbar_init(kv_full(s), 1);
@@ -220,7 +220,8 @@ attention_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap map, const Para
                     for (int i = 0; i < 32; ++i) o_run[hh * 32 + i] = fmaf(o_run[hh * 32 + i], beta, __uint_as_float(o[i]));
                 }
                 tc_fence_before();
-                mbar_arrive(o_empty(g));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_empty(g));
                 m_acc = m_blk;
             };
             for (int j = 0; j < p.nkb; ++j) {
@@ -278,8 +279,11 @@ attention_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap map, const Para
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
                 tc_fence_before();
-                mbar_arrive(p_full(g));
-                mbar_arrive(s_empty(g));
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(p_full(g));
+                    mbar_arrive(s_empty(g));
+                }
                 l_run = fmaf(l_run, ex2((m_run - m_new) * sl2), sum);           // m_run = -inf on the first block: factor 0
                 if (j > 0) fold_o(c - 1, m_run);                    // O of the previous block, relative to its max m_run
                 m_run = m_new;

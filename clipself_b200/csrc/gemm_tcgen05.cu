@@ -397,7 +397,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, uint32_t tadd
     }
 }
 
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG>
+// TN = true: both operands are consumed MN-major, i.e. A is stored [K][M] and W is stored [K][N] (the weight-gradient GEMM
+// dW = dY^T X reads dY [tokens][out] and X [tokens][in] as they are: no transposed copies).  A stage then holds 64-wide
+// atoms [64 k rows][64 m|n] of 8 KB each (UMMA canonical MN-major SWIZZLE_128B layout: LBO = atom pitch, SBO = 8 k rows).
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG, bool TN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_o16,
@@ -489,12 +492,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if constexpr (CG == 2) {
                         const uint32_t fb = map_to_cta(full_bar(stage), 0);
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-                        tma_load_2d_cg2(sa, &map_a, fb, kb * BLOCK_K, m0);
-                        tma_load_2d_cg2(sb, &map_b, fb, kb * BLOCK_K, n0);
+                        if constexpr (TN) {
+#pragma unroll
+                            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d_cg2(sa + a * 8192, &map_a, fb, m0 + a * 64, kb * BLOCK_K);
+#pragma unroll
+                            for (int b = 0; b < C::B_ROWS / 64; ++b) tma_load_2d_cg2(sb + b * 8192, &map_b, fb, n0 + b * 64, kb * BLOCK_K);
+                        } else {
+                            tma_load_2d_cg2(sa, &map_a, fb, kb * BLOCK_K, m0);
+                            tma_load_2d_cg2(sb, &map_b, fb, kb * BLOCK_K, n0);
+                        }
                     } else {
                         mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                        tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m0);
-                        tma_load_2d(sb, &map_b, full_bar(stage), kb * BLOCK_K, n0);
+                        if constexpr (TN) {
+#pragma unroll
+                            for (int a = 0; a < BLOCK_M / 64; ++a) tma_load_2d(sa + a * 8192, &map_a, full_bar(stage), m0 + a * 64, kb * BLOCK_K);
+#pragma unroll
+                            for (int b = 0; b < C::B_ROWS / 64; ++b) tma_load_2d(sb + b * 8192, &map_b, full_bar(stage), n0 + b * 64, kb * BLOCK_K);
+                        } else {
+                            tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m0);
+                            tma_load_2d(sb, &map_b, full_bar(stage), kb * BLOCK_K, n0);
+                        }
                     }
                     if (++stage == C::STAGES) {
                         stage = 0;
@@ -506,7 +523,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     } else if (warp == 1) {
         // ------------------------------ MMA issuer (CG = 2: leader CTA only) --------
         if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = make_idesc(CG * BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc = make_idesc(CG * BLOCK_M, BLOCK_N) | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // bits 15 / 16: A / B MN-major
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -523,15 +540,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t sa = base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + C::A_BYTES;
-                    const uint64_t da = make_smem_desc(sa);
-                    const uint64_t db = make_smem_desc(sb);
+                    // K-major: SBO = 1024 (8 rows), a k-step advances 16 bf16 = 32 B inside the swizzle atom: +2 in (addr >> 4).
+                    // MN-major (TN): LBO = 8192 (next 64-wide m|n atom), SBO = 1024 (next 8 k rows), a k-step = 16 k rows = 2048 B
+                    const uint64_t da = TN ? (make_smem_desc(sa) | ((uint64_t)(8192u >> 4) << 16)) : make_smem_desc(sa);
+                    const uint64_t db = TN ? (make_smem_desc(sb) | ((uint64_t)(8192u >> 4) << 16)) : make_smem_desc(sb);
+                    constexpr uint64_t kstep = TN ? (2048u >> 4) : 2u;
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr>>4)
                         if constexpr (CG == 2)
-                            umma_bf16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16_cg2(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         else
-                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     if constexpr (CG == 2) {
                         umma_commit_cg2(empty_bar(stage), 3);      // frees the slot in BOTH CTAs when the MMAs retire
@@ -593,7 +612,7 @@ static bool use_cta_pairs() {
     return v != 0;
 }
 
-template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG>
+template <int BLOCK_N, int MODE, bool OUT_BF16, int RES, bool LNFOLD, bool EMIT, int CG, bool TN = false>
 static int launch_cg(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t stream) {
     using C = Cfg<BLOCK_N, CG, EMIT>;
@@ -610,7 +629,7 @@ static int launch_cg(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N,
         const int rc = make_map_2d(&mo16, ep.out, 2, M, MODE == CS_EPI_SWIGLU ? N / 2 : N, ep.ldo, 32, 32, 64);
         if (rc) return rc;
     }
-    auto kern = gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, CG>;
+    auto kern = gemm_kernel<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, CG, TN>;
     static bool configured = false;
     if (!configured) {
         CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -642,6 +661,14 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb2, const CUtensorM
         if (use_cta_pairs()) return launch_cg<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, 2>(ma, mb2, M, N, K, ep, stream);
     }
     return launch_cg<BLOCK_N, MODE, OUT_BF16, RES, LNFOLD, EMIT, 1>(ma, mb1, M, N, K, ep, stream);
+}
+
+// weight-gradient form (both operands MN-major): plain f32 store or split-K red.add
+template <int BLOCK_N>
+static int dispatch_tn(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const EpiParams& ep, int res, cudaStream_t st) {
+    constexpr int CG = BLOCK_N == 256 ? 2 : 1;
+    if (res == RES_RED) return launch_cg<BLOCK_N, CS_EPI_STORE, false, RES_RED, false, false, CG, true>(ma, mb, M, N, K, ep, st);
+    return launch_cg<BLOCK_N, CS_EPI_STORE, false, RES_NONE, false, false, CG, true>(ma, mb, M, N, K, ep, st);
 }
 
 // mb2: B map with the box of a CTA pair member (BLOCK_N / 2 rows); mb: box of BLOCK_N rows (single-CTA kernel)
@@ -683,6 +710,33 @@ static int dispatch(const CUtensorMap& ma, const CUtensorMap& mb2, const CUtenso
 
 }  // namespace gemm
 }  // namespace cs
+
+// split-K factor for a plain f32 STORE: the one that minimises waves x (k-blocks per split + per-tile overhead)
+static void choose_split_k(cs::gemm::EpiParams& ep, int& res, int M, int N, int K, bool use256, int cg, int requested) {
+    using namespace cs;
+    using namespace cs::gemm;
+    const int num_kb = ceil_div(K, BLOCK_K);
+    const int tiles = ceil_div(M, cg * BLOCK_M) * ceil_div(N, use256 ? 256 : 128);
+    const int groups = num_sms() / cg;
+    int best = 1;
+    if (requested > 0) {
+        best = requested;
+    } else {
+        long long best_cost = -1;
+        for (int sp = 1; sp <= 16 && sp <= num_kb; ++sp) {
+            const long long waves = ceil_div((long long)tiles * sp, groups);
+            const long long cost = waves * (ceil_div(num_kb, sp) + 8);     // +8 k-blocks ~ per-tile epilogue/fill cost
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+        }
+    }
+    if (best > 1) {
+        ep.kb_per_split = ceil_div(num_kb, best);
+        ep.k_splits = ceil_div(num_kb, ep.kb_per_split);        // no empty split
+        ep.residual = reinterpret_cast<const float*>(ep.out);     // selects the red.add epilogue
+        ep.ldr = ep.ldo;
+        res = RES_RED;
+    }
+}
 
 extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int N,
                             int K, const cs_gemm_epilogue_t* e, void* stream) {
@@ -774,28 +828,44 @@ extern "C" int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
         // red.add into `out`, which the caller must have zeroed.  f32 STORE without residual only.
         CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual == nullptr && e->ln_stats == nullptr,
                      "cs_gemm_bf16: split-K needs a plain f32 STORE epilogue");
-        const int num_kb = ceil_div(K, BLOCK_K);
-        const int cg = (use256 && use_cta_pairs()) ? 2 : 1;            // work units and CTA groups of the kernel that will run
-        const int tiles = ceil_div(M, cg * BLOCK_M) * ceil_div(N, use256 ? 256 : 128);
-        const int groups = num_sms() / cg;
-        int best = 1;
-        if (e->reserved2 > 0) {
-            best = e->reserved2;
-        } else {
-            long long best_cost = -1;
-            for (int sp = 1; sp <= 16 && sp <= num_kb; ++sp) {
-                const long long waves = ceil_div((long long)tiles * sp, groups);
-                const long long cost = waves * (ceil_div(num_kb, sp) + 8);     // +8 k-blocks ~ per-tile epilogue/fill cost
-                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
-            }
-        }
-        if (best > 1) {
-            ep.kb_per_split = ceil_div(num_kb, best);
-            ep.k_splits = ceil_div(num_kb, ep.kb_per_split);        // no empty split
-            ep.residual = reinterpret_cast<const float*>(ep.out);     // selects the red.add epilogue
-            ep.ldr = ep.ldo;
-            res = RES_RED;
-        }
+        choose_split_k(ep, res, (int)M, N, K, use256, (use256 && use_cta_pairs()) ? 2 : 1, e->reserved2);
     }
     return use256 ? dispatch<256>(ma, mb2, mb, (int)M, N, K, ep, res, st) : dispatch<128>(ma, mb2, mb, (int)M, N, K, ep, res, st);
+}
+
+// C[M,N] (f32) = At^T . Bt  with At stored [K][M] (row stride lda) and Bt stored [K][N] (row stride ldb), both bf16: the
+// weight-gradient GEMM dW = dY^T X on dY [tokens][out] and X [tokens][in] as they lie in memory (train.py:104 backward of
+// every nn.Linear of the student, torch's addmm with transposed operands).  Epilogue: plain f32 STORE, optional alpha is
+// not applied; reserved2 selects split-K as in cs_gemm_bf16 (out must then be zeroed by the caller).
+extern "C" int cs_gemm_bf16_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, int64_t M, int N, int K,
+                               const cs_gemm_epilogue_t* e, void* stream) {
+    using namespace cs;
+    using namespace cs::gemm;
+    CS_CHECK_ARG(At && Bt && e && e->out, "cs_gemm_bf16_tn: null pointer");
+    CS_CHECK_ARG(M > 0 && N > 0 && K > 0 && M < (1ll << 31), "cs_gemm_bf16_tn: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+    CS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= M && ldb >= N, "cs_gemm_bf16_tn: lda/ldb must be multiples of 8 and >= M / N");
+    CS_CHECK_ARG(((uintptr_t)At % 16 == 0) && ((uintptr_t)Bt % 16 == 0), "cs_gemm_bf16_tn: operands must be 16 B aligned");
+    CS_CHECK_ARG(N % 32 == 0, "cs_gemm_bf16_tn: N must be a multiple of 32 (N=%d)", N);
+    CS_CHECK_ARG(e->mode == CS_EPI_STORE && e->out_dtype == CS_F32 && e->residual == nullptr && e->bias == nullptr &&
+                     e->ln_stats == nullptr && e->out2_bf16 == nullptr && e->alpha == 1.0f,
+                 "cs_gemm_bf16_tn: plain f32 STORE epilogue only");
+    CS_CHECK_ARG(((uintptr_t)e->out % 16 == 0) && e->ldo % 4 == 0, "cs_gemm_bf16_tn: out must be 16 B aligned with 16 B aligned rows");
+    EpiParams ep = {};
+    ep.mode = CS_EPI_STORE;
+    ep.out = e->out;
+    ep.ldo = e->ldo;
+    ep.alpha = 1.0f;
+    ep.dbg = e->reserved;
+    ep.k_splits = 1;
+    ep.kb_per_split = ceil_div(K, BLOCK_K);
+    const bool use256 = (N % 256 == 0);
+    CUtensorMap ma, mb;
+    int rc = make_map_bf16_2d(&ma, At, K, M, lda, 64, 64);        // box = [64 k rows][64 m]: one MN-major atom
+    if (rc) return rc;
+    rc = make_map_bf16_2d(&mb, Bt, K, N, ldb, 64, 64);
+    if (rc) return rc;
+    int res = RES_NONE;
+    if (e->reserved2 != 0) choose_split_k(ep, res, (int)M, N, K, use256, use256 ? 2 : 1, e->reserved2);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return use256 ? dispatch_tn<256>(ma, mb, (int)M, N, K, ep, res, st) : dispatch_tn<128>(ma, mb, (int)M, N, K, ep, res, st);
 }

@@ -47,11 +47,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (threadIdx.x >= 64 ? 2000000000ll : 4000000000ll)) {   // consumers report first
-            printf("clipself_b200: mbarrier wait timed out (smem 0x%x parity %u block %d thread %d)\n", bar, parity,
-                   (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
+        // (no printf here: inlined at every wait site it was a third of the attention kernels' code and cost
+        //  instruction-cache misses on the hot paths)
+        if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
 // Spinning variant (mbarrier.test_wait, no hardware suspend): lowest wake-up latency, for short handshakes on the critical path.
@@ -72,11 +70,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
     if (mbar_test_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_test_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("clipself_b200: mbarrier spin wait timed out (smem 0x%x parity %u block %d thread %d)\n", bar, parity,
-                   (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,

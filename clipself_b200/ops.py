@@ -215,6 +215,35 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, M: Optional[int] = None, N: Optio
     return out
 
 
+def gemm_tn(at: Tensor, bt: Tensor, out: Tensor, *, M: int, N: int, K: int, lda: Optional[int] = None,
+            ldb: Optional[int] = None, ldo: Optional[int] = None, k_splits: int = 0) -> Tensor:
+    """out[M,N] (f32) = at[K,M]^T @ bt[K,N]: the weight-gradient GEMM on operands stored tokens-major (no transposes).
+    k_splits as in gemm() (out must be pre-zeroed when != 0)."""
+    for name, x in (("at", at), ("bt", bt)):        # column-sliced views are fine: the leading dimension is explicit
+        if not x.is_cuda:
+            raise L.ClipselfB200Error(f"{name} must be a CUDA tensor (no CPU path exists)")
+        if x.dtype != torch.bfloat16:
+            raise TypeError(f"{name}: expected bf16, got {x.dtype}")
+    e = L.GemmEpilogue()
+    e.mode = L.EPI_STORE
+    e.out_dtype = _dt(out)
+    e.out = _p(out)
+    e.ldo = ldo if ldo is not None else out.shape[-1]
+    e.alpha = 1.0
+    e.reserved2 = k_splits
+    args = (_p(at), lda if lda is not None else at.stride(0), _p(bt), ldb if ldb is not None else bt.stride(0), M, N, K,
+            C.byref(e), _stream())
+    if GEMM_PROFILE is None:
+        call("cs_gemm_bf16_tn", *args)
+        return out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call("cs_gemm_bf16_tn", *args)
+    e1.record()
+    GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+    return out
+
+
 def pack_swiglu_weights(w1: Tensor, w2: Tensor, b1: Tensor, b2: Tensor, ldk: int) -> Tuple[Tensor, Tensor]:
     Hd, K = w1.shape
     rows = (Hd + 127) // 128 * 256

@@ -176,15 +176,10 @@ class _Tape:
         self.Mpad = Mpad
         self.dx = torch.empty(M, D, **f32)
         self.g_bf_D = torch.empty(M, D, **bf)            # bf16 copy of a [M,D] gradient
-        self.g_T_D = torch.empty(D, Mpad, **bf)          # and its transpose
-        self.act_T_D = torch.empty(D, Mpad, **bf)        # transpose of a saved [M,D] activation
         self.g_Hd = torch.empty(M, Hd, **bf)
         self.g_Hd2 = torch.empty(M, Hd, **bf)
-        self.act_T_Hd = torch.empty(Hd, Mpad, **bf)
         self.g_2Hd = torch.zeros(M, 2 * Hd, **bf)
-        self.g_T_2Hd = torch.empty(2 * Hd, Mpad, **bf)
         self.g_3D = torch.empty(M, 3 * D, **bf)
-        self.g_T_3D = torch.empty(3 * D, Mpad, **bf)
         self.g_D2 = torch.empty(M, D, **bf)
         self.delta = torch.empty(B * H * N, **f32)
         self.d_head = torch.empty(Mp, cfg.embed_dim, **f32)
@@ -428,30 +423,28 @@ class StudentEngine:
             pk, st = self.packs[i], t.stats[i]
             last = i == cfg.layers - 1
             # ---- MLP branch: x_out = xmid + w3(hln) + b3
-            ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
+            # weight gradients: dW = dY^T X on dY / X as they lie in memory (cs_gemm_bf16_tn: both operands MN-major)
+            ops.cast_transpose(dx, M, D, dst=t.g_bf_D)
             ops.col_reduce(dx, M, D, self.g(i, "mlp.w3.bias"), ws)
-            ops.cast_transpose(t.hln[i], M, self.Hp, dst_t=t.act_T_Hd)
             if not self.padded:
-                ops.gemm(t.g_T_D, t.act_T_Hd, self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M, k_splits=-1)       # dW3 = dx^T hln
+                ops.gemm_tn(t.g_bf_D, t.hln[i], self.g(i, "mlp.w3.weight"), M=D, N=Hd, K=M, k_splits=-1)    # dW3 = dx^T hln
             else:   # rows of the [D, 2730] gradient are not 16 B aligned: GEMM into a padded scratch, then copy
                 t.dw3_pad.zero_()
-                ops.gemm(t.g_T_D, t.act_T_Hd, t.dw3_pad, M=D, N=self.Hp, K=M, k_splits=-1)
+                ops.gemm_tn(t.g_bf_D, t.hln[i], t.dw3_pad, M=D, N=self.Hp, K=M, k_splits=-1)
                 self.g(i, "mlp.w3.weight").copy_(t.dw3_pad[:, :Hd])
             ops.gemm(t.g_bf_D, pk.w3T, t.g_Hd, M=M)                                               # d_hln
             ops.col_reduce(t.g_Hd, M, Hd, self.g(i, "mlp.ffn_ln.bias"), ws, x=t.h[i], mean=st[6], rstd=st[7],
                            dgamma=self.g(i, "mlp.ffn_ln.weight"))
             ops.layernorm_bwd_dx(t.g_Hd, t.h[i], M, Hd, st[6], st[7], self.p(i, "mlp.ffn_ln.weight"), t.g_Hd2)  # d_h
             ops.swiglu_bwd(t.x12[i], t.g_Hd2, M, Hd, t.g_2Hd, split=self.Hp if self.padded else True)   # d_x12
-            ops.cast_transpose(t.g_2Hd, M, 2 * self.Hp, dst_t=t.g_T_2Hd)
-            ops.cast_transpose(t.u2[i], M, D, dst_t=t.act_T_D)
             if not self.padded:
-                ops.gemm(t.g_T_2Hd, t.act_T_D, self._span(self.flat_grad, i, "mlp.w1.weight", 2 * Hd, D),
-                         M=2 * Hd, N=D, K=M, k_splits=-1)                                         # dW1|dW2
+                ops.gemm_tn(t.g_2Hd, t.u2[i], self._span(self.flat_grad, i, "mlp.w1.weight", 2 * Hd, D),
+                            M=2 * Hd, N=D, K=M, k_splits=-1)                                      # dW1|dW2
                 ops.col_reduce(t.g_2Hd, M, 2 * Hd, self._span(self.flat_grad, i, "mlp.w1.bias", 1, 2 * Hd).view(-1), ws)
             else:
                 Hp = self.Hp
-                ops.gemm(t.g_T_2Hd[:Hd], t.act_T_D, self.g(i, "mlp.w1.weight"), M=Hd, N=D, K=M, k_splits=-1)
-                ops.gemm(t.g_T_2Hd[Hp:Hp + Hd], t.act_T_D, self.g(i, "mlp.w2.weight"), M=Hd, N=D, K=M, k_splits=-1)
+                ops.gemm_tn(t.g_2Hd, t.u2[i], self.g(i, "mlp.w1.weight"), M=Hd, N=D, K=M, lda=2 * Hp, k_splits=-1)
+                ops.gemm_tn(t.g_2Hd[:, Hp:], t.u2[i], self.g(i, "mlp.w2.weight"), M=Hd, N=D, K=M, lda=2 * Hp, k_splits=-1)
                 ops.col_reduce(t.g_2Hd, M, Hd, self.g(i, "mlp.w1.bias"), ws, lddy=2 * Hp)
                 ops.col_reduce(t.g_2Hd[:, Hp:], M, Hd, self.g(i, "mlp.w2.bias"), ws, lddy=2 * Hp)
             ops.gemm(t.g_2Hd, pk.w12T, t.g_D2, M=M)                                               # d_u2
@@ -459,28 +452,24 @@ class StudentEngine:
                            dgamma=self.g(i, "norm2.weight"))
             ops.layernorm_bwd_dx(t.g_D2, t.xmid[i], M, D, st[4], st[5], self.p(i, "norm2.weight"), dx, add=dx)  # d_xmid
             # ---- attention branch: xmid = x + proj(aln) + b
-            ops.cast_transpose(dx, M, D, dst=t.g_bf_D, dst_t=t.g_T_D)
+            ops.cast_transpose(dx, M, D, dst=t.g_bf_D)
             ops.col_reduce(dx, M, D, self.g(i, "attn.proj.bias"), ws)
-            ops.cast_transpose(t.aln[i], M, D, dst_t=t.act_T_D)
-            ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.proj.weight"), M=D, N=D, K=M, k_splits=-1)  # dWproj
+            ops.gemm_tn(t.g_bf_D, t.aln[i], self.g(i, "attn.proj.weight"), M=D, N=D, K=M, k_splits=-1)  # dWproj
             ops.gemm(t.g_bf_D, pk.wprojT, t.g_D2, M=M)                                            # d_aln
             ops.col_reduce(t.g_D2, M, D, self.g(i, "attn.inner_attn_ln.bias"), ws, x=t.att[i], mean=st[2], rstd=st[3],
                            dgamma=self.g(i, "attn.inner_attn_ln.weight"))
             d_att = t.g_bf_D
             ops.layernorm_bwd_dx(t.g_D2, t.att[i], M, D, st[2], st[3], self.p(i, "attn.inner_attn_ln.weight"), d_att)
-            ops.cast_transpose(t.u[i], M, D, dst_t=t.act_T_D)
             if not last:
                 ops.attention_bwd(t.qkv[i], t.att[i], d_att, t.lse[i], B, N, H, self.scale,
                                   (res.rope_cos, res.rope_sin), t.delta, t.g_3D)                    # d_qkv (raw projections)
-                ops.cast_transpose(t.g_3D, M, 3 * D, dst_t=t.g_T_3D)
-                ops.gemm(t.g_T_3D, t.act_T_D, self._span(self.flat_grad, i, "attn.q_proj.weight", 3 * D, D),
-                         M=3 * D, N=D, K=M, k_splits=-1)                                          # dWq|dWk|dWv
+                ops.gemm_tn(t.g_3D, t.u[i], self._span(self.flat_grad, i, "attn.q_proj.weight", 3 * D, D),
+                            M=3 * D, N=D, K=M, k_splits=-1)                                       # dWq|dWk|dWv
                 ops.col_reduce(t.g_3D, M, D, self.g(i, "attn.q_bias"), ws, lddy=3 * D)
                 ops.col_reduce(t.g_3D[:, 2 * D:], M, D, self.g(i, "attn.v_bias"), ws, lddy=3 * D)
                 ops.gemm(t.g_3D, pk.wqkvT, t.g_D2, M=M)                                           # d_u
             else:
-                ops.cast_transpose(d_att, M, D, dst_t=t.g_T_D)
-                ops.gemm(t.g_T_D, t.act_T_D, self.g(i, "attn.v_proj.weight"), M=D, N=D, K=M, k_splits=-1)
+                ops.gemm_tn(d_att, t.u[i], self.g(i, "attn.v_proj.weight"), M=D, N=D, K=M, k_splits=-1)
                 ops.col_reduce(d_att, M, D, self.g(i, "attn.v_bias"), ws)
                 ops.gemm(d_att, pk.wvT, t.g_D2, M=M)
             ops.col_reduce(t.g_D2, M, D, self.g(i, "norm1.bias"), ws, x=t.x[i], mean=st[0], rstd=st[1],

@@ -105,7 +105,7 @@ class CLIPSelf:
             if self._cropper is None:
                 self._cropper = _BatchCropper()
             images, crops = self._cropper(raw, device)
-            crops = crops.to(dtype)
+            crops = self._cropper.cast(crops, dtype)
         else:
             images, normed_boxes, image_crops = batch       # texts are not paired with images
             B, K = normed_boxes.shape[:2]

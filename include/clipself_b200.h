@@ -223,6 +223,15 @@ typedef struct {
 int cs_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int N, int K,
                  const cs_gemm_epilogue_t* epi, void* stream);
 
+/* C[M,N] (f32) = At^T · Bt with BOTH operands stored reduction-major: At [K, M] (row stride lda), Bt [K, N] (row stride
+ * ldb), bf16.  This is the weight gradient of every nn.Linear of the student (the autograd backward of
+ * eva_vit_model.py:177-179, 220, 98-105 under train.py:104): dW[out,in] = dY[tokens,out]^T · X[tokens,in] reads dY and X
+ * as they lie in memory — the tensor cores take both tiles MN-major, no transposed copies are made.
+ * Epilogue: plain f32 STORE only (mode STORE, no bias / residual / folding); epi->reserved2 selects split-K exactly as
+ * in cs_gemm_bf16 (-1 = choose; `out` must then be zero on entry, partial products are accumulated with red.add). */
+int cs_gemm_bf16_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, int64_t M, int N, int K,
+                    const cs_gemm_epilogue_t* epi, void* stream);
+
 /* Pack the SwiGLU gate/up weights so that one GEMM tile holds matching x1/x2 columns:
  *   packed row (t*2*half + j)        = w1 row (t*half + j)
  *   packed row (t*2*half + half + j) = w2 row (t*half + j),   half = 128, j < half

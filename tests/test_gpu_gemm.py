@@ -147,6 +147,23 @@ def test_gemm_split_k(dev, M, N, K, splits):
     assert ok, msg
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(768, 2048, 12608, -1), (2304, 768, 12608, 0), (2730, 1024, 9232, -1), (100, 128, 1000, 2),
+                                          (768, 768, 197, 0), (4096, 768, 12608, 4)])
+def test_gemm_tn_weight_gradient(dev, M, N, K, splits):
+    """dW[M,N] = dY[K,M]^T X[K,N] on operands stored tokens-major (both MN-major on the tensor cores), against torch; also
+    with a column-sliced dY (lda > M), the padded-SwiGLU case of the student backward."""
+    from clipself_b200 import ops
+    g = torch.Generator().manual_seed(11 + M + K)
+    lda = (M + 7) // 8 * 8 + 16
+    dy = torch.randn(K, lda, generator=g).to(torch.bfloat16).to(dev)
+    x = torch.randn(K, N, generator=g).to(torch.bfloat16).to(dev)
+    out = torch.zeros(M, N, device=dev)
+    ops.gemm_tn(dy[:, 8:], x, out, M=M, N=N, K=K, lda=lda, k_splits=splits)
+    ref = dy[:, 8:8 + M].float().t() @ x.float()
+    ok, msg = _report(f"tn {M}x{N}x{K} splits={splits}", out, ref, 2e-3)
+    assert ok, msg
+
+
 @pytest.mark.parametrize("M,N,K,parts", [(1000, 768, 2048, 16), (3000, 768, 768, 24), (300, 128, 128, 4)])
 def test_gemm_ln_fold(dev, M, N, K, parts):
     """y = x + LN(a) W^T + b computed as rstd*(a W'^T - mean*c1) + c2 from partial row statistics."""
