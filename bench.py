@@ -270,10 +270,19 @@ def run_b200(args):
     dev_crops = None
     if wl["kind"] == "grid" and not wl.get("mask_pool"):
         raw_batch = synth_raw_image_batch(cfg, B, K, seed=4321 + rank, det=wl.get("det"))
-        for _ in range(3):
+        for _ in range(4):
             step(raw_batch)
+        enc0 = int(_lib.lib().cs_tensor_map_encodes())
+        if os.environ.get("BENCH_PROFILE_RAW"):         # development: where does the host spend the raw-batch step?
+            import cProfile, pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            timed(raw_batch, 5, read_loss=True)
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
         dc_ms, _ = timed(raw_batch, args.steps, read_loss=True)
         dev_crops = {"value": round(world * B / (dc_ms / args.steps / 1e3), 2), "unit": "images/sec",
+                     "tensor_map_encodes_in_timed_region": int(_lib.lib().cs_tensor_map_encodes()) - enc0,
                      "h2d_bytes_per_step": int(raw_batch.host_bytes()), "d2h_bytes_per_step": 4,
                      "ms_per_step": round(dc_ms / args.steps, 3),
                      "input": "decoded uint8 480x640 images + grid boxes; K bicubic crops/img and the student image made on the GPU "

@@ -128,8 +128,22 @@ def call(name: str, *args) -> None:
     launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
+_device_info = {}
+
+
 def require_device() -> dict:
-    """Raise unless the current CUDA device is an sm_100 part."""
+    """Raise unless the current CUDA device is an sm_100 part.  The answer is cached per device once it is positive:
+    cs_device_info queries the device properties, which costs 10 ms and more per call (it sat in the per-step crop path)."""
+    try:
+        import torch
+        key = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    except Exception:           # noqa: BLE001
+        key = -1
+    if key >= 0 and key in _device_info:
+        return _device_info[key]
     sm, n, mem = i32(), i32(), i64()
     call("cs_device_info", C.byref(sm), C.byref(n), C.byref(mem))
-    return dict(sm=sm.value, num_sms=n.value, hbm_bytes=mem.value)
+    info = dict(sm=sm.value, num_sms=n.value, hbm_bytes=mem.value)
+    if key >= 0:
+        _device_info[key] = info
+    return info

@@ -336,10 +336,12 @@ class EVAVisionTransformer(nn.Module):
         from .tower import chunk_schedule
         return chunk_schedule(R, min(self._infer_engine().chunk_images, max(R, 1)))
 
-    def forward_chunked(self, x: Tensor, events) -> Tensor:
+    def forward_chunked(self, x: Tensor, events, out: Optional[Tensor] = None) -> Tensor:
         """forward() on a crop tensor that is still being filled by an H2D stream: piece k of
-        teacher_chunk_schedule() may be read once events[k] has completed (see training/clipself.py)."""
-        return self._infer_engine().forward_cls(x, ready_events=events)
+        teacher_chunk_schedule() may be read once events[k] has completed (see training/clipself.py).  events = None:
+        the tensor is complete.  `out`: caller-owned [R, embed_dim] f32 result buffer (a stable address keeps the
+        native tower's per-(buffers, shape) CUDA graphs hot)."""
+        return self._infer_engine().forward_cls(self._prep(x) if events is None else x, out=out, ready_events=events)
 
     def _prep(self, x: Tensor) -> Tensor:
         if x.dtype not in (torch.float32, torch.bfloat16):

@@ -33,6 +33,7 @@ class CLIPSelf:
         self._images_dev = None
         self._images_free = None
         self._cropper = None
+        self._teacher_out = None
 
     def _stream_inputs(self, images, image_crops, valid, R, device, dtype, pieces):
         """Host->device copies of one step on a side stream, in the order the step consumes them: the
@@ -155,11 +156,14 @@ class CLIPSelf:
 
         def run_teacher():
             with torch.no_grad():
+                # the features land in a buffer this plug-in owns (consumed by the loss and its backward within the step)
+                edim = dist_model.visual.cfg.embed_dim
+                if self._teacher_out is None or self._teacher_out.shape[0] < R or self._teacher_out.device != device:
+                    self._teacher_out = torch.empty(max(R, 1), edim, device=device, dtype=torch.float32)
+                feats = dist_model.visual.forward_chunked(crops, crop_events, out=self._teacher_out[:R])
                 if crop_events is not None:
-                    feats = dist_model.visual.forward_chunked(crops, crop_events)
                     self._crops_free.record()
-                    return feats
-                return dist_model.encode_image(crops, normalize=False)
+                return feats
 
         # Order: normally the student forward goes first (it only needs the small images, so it overlaps the crop H2D
         # stream).  With the overlapped gradient exchange the frozen teacher goes first: it does not depend on the weights
