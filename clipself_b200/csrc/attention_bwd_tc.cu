@@ -1,6 +1,7 @@
-// EXPERIMENTAL (off by default, enabled with CS_ATTN_BWD_TC=1; NOT yet run on hardware — staged for round 2,
-// see DESIGN.md §9): tcgen05 attention backward for head_dim 64 and any sequence length, the tensor-core
-// counterpart of attention_bwd_{dq,dkv}_kernel in attention.cu (autograd of eva_vit_model.py:206-217).
+// tcgen05 attention backward for head_dim 64 and any sequence length (autograd of eva_vit_model.py:206-217): the default
+// behind cs_attention_bwd for every shape; the mma.sync kernels of round 1 (attention.cu) only run with CS_ATTN_LEGACY=1.
+// Measured on a B200 (profiles/r02_attention_experiments.txt): 429 us at B=64 N=197 (slower than the mma.sync pair, 307 us),
+// 451 us at B=16 N=577, 1052 us at B=2 N=4097 (1.6x faster).
 //
 // Like the mma.sync version it is two passes that recompute P from the saved log-sum-exp, so neither needs
 // a running softmax or atomics; both are instances of ONE streamed-operand template:

@@ -280,6 +280,12 @@ class EVAVisionTransformer(nn.Module):
         if first == len(flags) or flags != mixed or not all(flags[first:]):
             raise NotImplementedError("the fused training path needs a trainable suffix of whole blocks "
                                       "(lock_image_tower(unlocked_groups=n) unfreezes blocks[-n:], as the reference does)")
+        stray = [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("blocks.")]
+        if stray:
+            # the reference would train these (main.py:199-213 puts every requires_grad parameter in the optimizer); this
+            # path treats everything outside the blocks as frozen, so refuse instead of silently not updating them
+            raise NotImplementedError(f"trainable parameters outside the transformer blocks are not supported: {stray[:4]} ...; "
+                                      "call lock_image_tower(unlocked_groups=n) (every CLIPSelf script passes --lock-image)")
         if self._student is None:
             self._student = StudentEngine(self.cfg, self._tower_sd(), self._device())
         eng = self._student
