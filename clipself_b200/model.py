@@ -350,6 +350,8 @@ class EVAVisionTransformer(nn.Module):
         return self._infer_engine().forward_cls(self._prep(x) if events is None else x, out=out, ready_events=events)
 
     def _prep(self, x: Tensor) -> Tensor:
+        if x.dim() == 4:
+            input_grid(x, self.cfg)           # shape errors first (ValueError), before any engine is chosen
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
         return x.contiguous()
