@@ -55,6 +55,7 @@ PROTOTYPES = {
     "cs_gemm_bf16_tn": [vp, i64, vp, i64, i64, i32, i32, C.POINTER(GemmEpilogue), vp],
     "cs_pack_swiglu_weights": [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, vp],
     "cs_attention_fwd": [vp, i32, i32, i32, f32, vp, vp, vp, vp],
+    "cs_attention_cls_fwd": [vp, i32, i32, i32, f32, vp, vp, vp],
     "cs_cast_pad_bf16": [vp, i64, i64, i64, vp, i64, vp],
     "cs_attention_bwd": [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp],
     "cs_cast_transpose_bf16": [vp, i32, i64, i32, i64, vp, i64, vp, i64, vp],

@@ -72,6 +72,7 @@ struct cs_tower {
     std::map<cs::tower::GraphKey, std::pair<int, cudaGraphExec_t>> graphs;     // (times seen, executable)
     std::mutex mu;
     bool use_graphs;
+    bool cls_tail = true;                       // last block of cs_vit_forward_cls on the CLS rows only (CLIPSELF_FULL_LAST_BLOCK=1: off)
     cudaStream_t capture_stream = nullptr;      // graphs are captured here (the legacy default stream cannot be captured)
 };
 
@@ -402,6 +403,84 @@ static int block(const cs_tower* t, const GridCtx& gc, int grid, int i, int n, c
     return cs_gemm_bf16(w.h, Hp, b.w3_f, Hp, M, D, Hp, &o, st);
 }
 
+// The LAST block of a tower that is read at the CLS token only (encode_image: head(norm(x)[:, 0]), eva_vit_model.py:565-569):
+// K and V need every token, so the QKV GEMM is unchanged, but attention, proj, the SwiGLU MLP and w3 run on the n CLS rows
+// instead of n x N rows (same kernels, same folding; ~72 % of one block's work disappears).  The compact CLS-row buffers
+// live in scratch that the folded CLS path does not use otherwise (w.att, w.stats_att, w.u).  x_cls: the new residual
+// stream of the CLS rows, [n, D] f32, which the caller normalises and projects.
+struct ClsTail {
+    float *x, *stats_x, *stats_h;
+    __nv_bfloat16 *xb, *h;
+};
+static bool carve_cls_tail(const Cfg& g, int n, int N, const Workspace& w, ClsTail* c) {
+    const int D = g.width, Hp = g.hidden_pad();
+    Carver cv{reinterpret_cast<uint8_t*>(w.u)};
+    c->x = cv.take<float>((int64_t)n * D);
+    c->xb = cv.take<__nv_bfloat16>((int64_t)n * D);
+    c->h = cv.take<__nv_bfloat16>((int64_t)n * Hp);
+    c->stats_x = cv.take<float>((int64_t)n * stat_parts(D) * 2);
+    c->stats_h = cv.take<float>((int64_t)n * (Hp / 64) * 2);
+    return cv.off <= (int64_t)n * N * D * 2 && N <= 1024;        // w.u holds n x N x D bf16
+}
+static int block_cls_tail(const cs_tower* t, const GridCtx& gc, int grid, int i, int n, const Workspace& w, const ClsTail& c, void* st) {
+    const Cfg& g = t->cfg;
+    const BlockPack& b = t->blocks[i];
+    const int N = grid * grid + 1, D = g.width, Hp = g.hidden_pad();
+    const int64_t M = (int64_t)n * N;
+    int rc;
+    auto fold = [&](cs_gemm_epilogue_t& e, const float* stats, const float* c1, int parts, int dim) {
+        e.ln_stats = stats;
+        e.ln_c1 = c1;
+        e.ln_parts = parts;
+        e.ln_dim = dim;
+        e.ln_eps = g.ln_eps;
+    };
+    auto emit_cls = [&](cs_gemm_epilogue_t& e, const float* residual, int64_t ldr) {
+        e.mode = CS_EPI_STORE;
+        e.out_dtype = CS_F32;
+        e.out = c.x;
+        e.ldo = D;
+        e.residual = residual;
+        e.ldr = ldr;
+        e.out2_bf16 = c.xb;
+        e.ldo2 = D;
+        e.stats_out = c.stats_x;
+    };
+    cs_gemm_epilogue_t e = epi0();              // q | k | v of every token (k, v feed the CLS query)
+    e.mode = CS_EPI_QKV_ROPE;
+    e.out_dtype = CS_BF16;
+    e.out = w.qkv;
+    e.ldo = 3 * D;
+    e.bias = b.c2_qkv;
+    e.rope_pos = gc.rope_pos;
+    e.rope_freq = t->rope_freq;
+    e.rope_grid = grid;
+    e.tokens = N;
+    e.rope_cols = 2 * D;
+    fold(e, w.stats_x, b.c1_qkv, stat_parts(D), D);
+    if ((rc = cs_gemm_bf16(w.xb, D, b.wqkv_f, D, M, 3 * D, D, &e, st))) return rc;
+    if ((rc = cs_attention_cls_fwd(w.qkv, n, N, g.heads, 0.125f, w.att, w.stats_att, st))) return rc;     // -> [n, D], [n, 4H, 2]
+    cs_gemm_epilogue_t p = epi0();              // x_cls = x[CLS rows] + inner_attn_ln-fold(att_cls Wproj'^T)
+    emit_cls(p, w.x, (int64_t)N * D);
+    p.bias = b.c2_proj;
+    fold(p, w.stats_att, b.c1_proj, 4 * g.heads, D);
+    if ((rc = cs_gemm_bf16(w.att, D, b.wproj_f, D, n, D, D, &p, st))) return rc;
+    cs_gemm_epilogue_t s = epi0();
+    s.mode = CS_EPI_SWIGLU;
+    s.out_dtype = CS_BF16;
+    s.out = c.h;
+    s.ldo = Hp;
+    s.bias = b.c2_w12;
+    s.stats_out = c.stats_h;
+    fold(s, c.stats_x, b.c1_w12, stat_parts(D), D);
+    if ((rc = cs_gemm_bf16(c.xb, D, b.w12_f, D, n, 2 * Hp, D, &s, st))) return rc;
+    cs_gemm_epilogue_t o = epi0();              // x_cls += ffn_ln-fold(h_cls W3'^T), in place
+    emit_cls(o, c.x, D);
+    o.bias = b.c2_w3;
+    fold(o, c.stats_h, b.c1_w3, Hp / 64, g.hidden);
+    return cs_gemm_bf16(c.h, Hp, b.w3_f, Hp, n, D, Hp, &o, st);
+}
+
 enum Kind { KIND_CLS = 0, KIND_DENSE = 1 };
 
 static int run_chunk(const cs_tower* t, const GridCtx& gc, int grid, int kind, const void* images, cs_dtype_t dtype, int n,
@@ -410,15 +489,22 @@ static int run_chunk(const cs_tower* t, const GridCtx& gc, int grid, int kind, c
     const int N = grid * grid + 1, D = g.width;
     int rc;
     if ((rc = embed(t, gc, grid, images, dtype, n, w, st))) return rc;
-    for (int i = 0; i < g.layers; ++i)
-        if ((rc = block(t, gc, grid, i, n, w, kind == KIND_CLS || i + 1 < g.layers, st))) return rc;
+    ClsTail ct;
+    const bool cls_tail = kind == KIND_CLS && t->cls_tail && carve_cls_tail(g, n, N, w, &ct);
+    for (int i = 0; i < g.layers; ++i) {
+        if (cls_tail && i + 1 == g.layers) rc = block_cls_tail(t, gc, grid, i, n, w, ct, st);
+        else rc = block(t, gc, grid, i, n, w, kind == KIND_CLS || i + 1 < g.layers, st);
+        if (rc) return rc;
+    }
     cs_gemm_epilogue_t e = epi0();
     e.mode = CS_EPI_STORE;
     e.out_dtype = CS_F32;
     e.bias = t->head_b;
     e.ldo = g.embed_dim;
     if (kind == KIND_CLS) {        // norm(x)[:, 0] -> head (eva_vit_model.py:565-569)
-        if ((rc = cs_layernorm_fwd(w.x, CS_F32, D, n, D, 0, N, 0, t->norm_g, t->norm_b, g.ln_eps, w.cls_ln, D, nullptr, nullptr, st))) return rc;
+        if (cls_tail) rc = cs_layernorm_fwd(ct.x, CS_F32, D, n, D, 0, 1, 0, t->norm_g, t->norm_b, g.ln_eps, w.cls_ln, D, nullptr, nullptr, st);
+        else rc = cs_layernorm_fwd(w.x, CS_F32, D, n, D, 0, N, 0, t->norm_g, t->norm_b, g.ln_eps, w.cls_ln, D, nullptr, nullptr, st);
+        if (rc) return rc;
         e.out = out;
         return cs_gemm_bf16(w.cls_ln, D, t->head_w, D, n, g.embed_dim, D, &e, st);
     }
@@ -565,6 +651,10 @@ extern "C" int cs_pack_weights_create(const cs_tower_cfg_t* cfg, const char* con
     t->cfg = to_cfg(cfg);
     const char* e = getenv("CLIPSELF_NO_GRAPH");
     t->use_graphs = !(e != nullptr && e[0] != '\0' && e[0] != '0');
+    {
+        const char* f = getenv("CLIPSELF_FULL_LAST_BLOCK");
+        t->cls_tail = !(f != nullptr && f[0] != '\0' && f[0] != '0');
+    }
     Carver c{(uint8_t*)pack_buffer};
     carve(t, c);
     rc = pack(t, names, tensors_f32, count, (cudaStream_t)stream);

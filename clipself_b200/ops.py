@@ -260,6 +260,14 @@ def attention_fwd(qkv: Tensor, B: int, N: int, H: int, scale: float, out: Tensor
     return out
 
 
+def attention_cls_fwd(qkv: Tensor, B: int, N: int, H: int, scale: float, out_cls: Tensor,
+                      row_stats_cls: Optional[Tensor] = None) -> Tensor:
+    """softmax(q_cls k^T * scale) v for the CLS query of every (image, head): qkv [B*N, 3*H*64] -> out_cls [B, H*64]."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    call("cs_attention_cls_fwd", _p(qkv), B, N, H, float(scale), _p(out_cls), _p(row_stats_cls), _stream())
+    return out_cls
+
+
 def cast_pad_bf16(src: Tensor, ldd: Optional[int] = None) -> Tensor:
     _chk(src, torch.float32, "src")
     src2 = src.reshape(src.shape[0], -1)

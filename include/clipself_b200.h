@@ -300,6 +300,13 @@ int cs_swiglu_fwd(const void* x12_bf16, int64_t M, int Hd, int64_t ld12, void* h
 int cs_swiglu_bwd(const void* x12_bf16, const void* dh_bf16, int64_t M, int Hd, int64_t ld12,
                   int64_t lddh, void* dx12_bf16, int split_layout, void* stream);
 
+/* Attention for the CLS query only: qkv [B*N, 3*H*64] bf16 (CLS = row 0 of each image) -> out_cls [B, H*64] bf16 and,
+ * optionally, row_stats_cls [B, 4H, 2] (sum / sum of squares per 16-dim quarter of the f32 output, for the folded
+ * inner_attn_ln).  eva_vit_model.py:206-217 for the LAST block of a tower that is read at the CLS token only
+ * (encode_image, eva_vit_model.py:565-569): cs_vit_forward_cls runs that block on the CLS rows alone.  N <= 1024. */
+int cs_attention_cls_fwd(const void* qkv_bf16, int B, int N, int H, float scale, void* out_cls_bf16, float* row_stats_cls,
+                         void* stream);
+
 /* Fused AdamW over a flat f32 buffer — torch.optim.AdamW semantics as configured at
  * main.py:205-213 (decoupled weight decay, bias correction); grad is multiplied by grad_scale
  * first (1/world_size after a sum all-reduce). `step` is 1-based. */

@@ -88,6 +88,31 @@ def test_attention_fwd(dev, B, N, H):
         torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-2, atol=5e-2)
 
 
+@pytest.mark.parametrize("B,N,H", [(5, 197, 12), (3, 17, 2), (2, 577, 16), (2, 1024, 1), (9, 33, 3)])
+def test_attention_cls_fwd(dev, B, N, H):
+    """The CLS-query attention of the teacher's last block (cs_attention_cls_fwd) against torch and against row 0 of the
+    full attention kernel."""
+    from clipself_b200 import ops
+    D = H * 64
+    torch.manual_seed(31 * B + N + H)
+    qkv = torch.randn(B * N, 3 * D, device=dev).to(torch.bfloat16)
+    out = torch.full((B, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    stats = torch.full((B, 4 * H, 2), float("nan"), device=dev)
+    ops.attention_cls_fwd(qkv, B, N, H, 0.125, out, stats)
+    q, k, v = (t.reshape(B, N, H, 64).permute(0, 2, 1, 3) for t in qkv.float().view(B, N, 3, D).unbind(2))
+    s = (q[:, :, :1] @ k.transpose(-1, -2)) * 0.125
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, D)
+    err = (out.float() - ref).abs().max().item()
+    print(f"cls attention B={B} N={N} H={H}: max err {err:.4e}")
+    assert err < 1e-2
+    o = ref.view(B, 4 * H, 16)
+    torch.testing.assert_close(stats[..., 0], o.sum(-1), rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(stats[..., 1], (o * o).sum(-1), rtol=1e-2, atol=2e-2)
+    full = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
+    ops.attention_fwd(qkv, B, N, H, 0.125, full)
+    assert (out.float() - full.view(B, N, D)[:, 0].float()).abs().max().item() < 8e-3      # same rounding points, other summation order
+
+
 @pytest.mark.parametrize("hin,hout", [(1024, 320), (896, 672), (64, 160), (224, 224), (37, 53)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_resize_bilinear(dev, hin, hout, dtype):
