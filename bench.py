@@ -49,15 +49,18 @@ WORKLOADS = {
 }
 
 
-def flops_per_image(cfg, K, det=None):
+def flops_per_image(cfg, K, det=None, executed=False):
     """F_step = K*F_teacher + 3*F_student_dense (2*M*N*K convention); `det` = student
-    resolution when it differs from the tower's own."""
+    resolution when it differs from the tower's own.  executed=True: what the kernels actually do — the teacher's last
+    block runs on the CLS row only, which the reference's algorithmic count does not know."""
     D, Hd, C, L = cfg.width, cfg.hidden, cfg.embed_dim, cfg.layers
 
     def tower(N, dense):
         pe = 2 * (N - 1) * (3 * cfg.patch ** 2) * D
         blk = 8 * N * D * D + 4 * N * N * D + 6 * N * D * Hd
         if not dense:
+            if executed:        # last block: q|k|v of every token, then one query row through attention, proj and the MLP
+                return pe + (L - 1) * blk + 6 * N * D * D + 4 * N * D + 2 * D * D + 6 * D * Hd + 2 * D * C
             return pe + L * blk + 2 * D * C
         return pe + (L - 1) * blk + 4 * N * D * D + 6 * N * D * Hd + 2 * (N - 1) * D * C
 
@@ -320,6 +323,7 @@ def run_b200(args):
     e2e_value = world * B / (e2e_ms / args.steps / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     step_tflops = value * flops_per_image(cfg, K, wl.get("det")) / 1e12
+    cls_tail = os.environ.get("CLIPSELF_FULL_LAST_BLOCK", "0") in ("", "0") and os.environ.get("CLIPSELF_PY_TOWER") is None
     h2d = sum(t.numel() * t.element_size() for t in host_batch)
     out = {
         "metric": f"images/sec ({K} boxes/img) {('ViT-B/16@224' if cfg.width == 768 else 'ViT-L/14@336') + (f' student@{wl["det"]}' if wl.get('det') else '')} distill step", "value": round(value, 2), "unit": "images/sec",
@@ -330,6 +334,7 @@ def run_b200(args):
                    "global_batch": world * B, "boxes_per_image": K, "parallelism": f"dp{world}",
                    "l2_policy": f"inputs larger than L2 (crops {host_batch[2].numel() * 4 / 1e9:.2f} GB/step vs 126 MB L2), no explicit flush",
                    "step_tflops": round(step_tflops, 1), "step_frac_of_peak": round(step_tflops / (world * peak_tf), 4),
+                   "step_tflops_executed": round(value * flops_per_image(cfg, K, wl.get("det"), executed=cls_tail) / 1e12, 1),
                    "last_loss": float(last_loss.detach())},
         "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_copy_alone_gbs": round(h2d_gbs, 1)},

@@ -6,7 +6,7 @@ O=gpurun_out/r3z; mkdir -p $O
 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 | tee $O/pytest_gpu.txt
 timeout 500 python bench.py --steps 20 --warmup 3 2>$O/bench_cfg2.err | tail -1 > $O/bench_cfg2.json; cut -c1-300 $O/bench_cfg2.json
 for w in cfg4 cfg5 recipe_b16; do timeout 400 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu 2>/dev/null | tail -1 > $O/bench_$w.json; cut -c1-200 $O/bench_$w.json; done
-CLIPSELF_NO_GRAPH=1 CLIPSELF_PY_TOWER=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches.csv python bench.py --workload cfg2 --profile-one-step > $O/ncu_launches.log 2>&1
+CLIPSELF_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches.csv python bench.py --workload cfg2 --profile-one-step > $O/ncu_launches.log 2>&1
 python tools/ncu_summarize.py $O/launches.csv > $O/launches_summary.txt; head -24 $O/launches_summary.txt
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_fwd_tc4 -s 2 -c 1 -o $O/attn_tc4 python tools/attn_one.py 512 197 12 > $O/ncu_attn.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:gemm_kernel -s 1 -c 1 -o $O/gemm_swiglu_fold python tools/gemm_one.py swiglu_fold 512 > $O/ncu_gemm1.log 2>&1
