@@ -2,7 +2,7 @@
 # round-2 final measurement pass: full GPU suite, bench lines of every workload, ncu launch list of one cfg2 step,
 # ncu --set full of the attention kernel and the two dominant GEMM instantiations at the step's shape, region kernels
 cd "$(dirname "$0")/.."
-O=gpurun_out/r3z; mkdir -p $O
+O=gpurun_out/final_pass; mkdir -p $O
 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 | tee $O/pytest_gpu.txt
 timeout 500 python bench.py --steps 20 --warmup 3 2>$O/bench_cfg2.err | tail -1 > $O/bench_cfg2.json; cut -c1-300 $O/bench_cfg2.json
 for w in cfg4 cfg5 recipe_b16; do timeout 400 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu 2>/dev/null | tail -1 > $O/bench_$w.json; cut -c1-200 $O/bench_$w.json; done
