@@ -95,6 +95,40 @@ def test_vit_forward_through_the_c_abi(golden, tag):
     assert lib.cs_pack_weights_destroy(teacher) == 0 and lib.cs_pack_weights_destroy(student) == 0
 
 
+@pytest.mark.parametrize("tag", ["tiny_grid", "cfg1_b16"])
+def test_cls_only_last_block_equals_the_full_block(tag, monkeypatch):
+    """cs_vit_forward_cls runs the last block on the CLS rows only (encode_image reads norm(x)[:, 0], eva_vit_model.py:565-569):
+    the result must be the one of the full block (CLIPSELF_FULL_LAST_BLOCK=1) up to the summation order of the CLS-query
+    attention kernel."""
+    from clipself_b200 import _lib as L
+    lib = L.lib()
+    L.require_device()
+    ocfg, B, K, kind, ragged = CASES[tag]
+    dev = torch.device("cuda")
+    _, boxes, crops = O.synth_batch(ocfg, B, K, 77, kind=kind, ragged=ragged)
+    _, idx = O.extract_rois(boxes)
+    tc = crops.flatten(0, 1)[idx].to(dev).contiguous()
+    n = tc.shape[0]
+    sd = O.synth_tower_weights(ocfg, 78)
+    outs = []
+    for full in ("1", "0"):
+        monkeypatch.setenv("CLIPSELF_FULL_LAST_BLOCK", full)            # read when the handle is created
+        cfg, tower, pack = _create(lib, L, ocfg, sd, dev)
+        need = C.c_int64(0)
+        assert lib.cs_query_workspace(C.byref(cfg), n, 0, C.byref(need)) == 0
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        out = torch.full((n, ocfg.embed_dim), float("nan"), device=dev)
+        rc = lib.cs_vit_forward_cls(tower, tc.data_ptr(), L.CS_F32, n, ws.data_ptr(), need.value, n, out.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.cs_last_error().decode()
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+        assert lib.cs_pack_weights_destroy(tower) == 0
+    r = _rel(outs[1].cpu().numpy(), outs[0].cpu().numpy())
+    print(f"{tag}: CLS-only last block vs full last block rel-L2 {r:.3e}")
+    assert torch.isfinite(outs[1]).all() and r <= 2e-3
+
+
 def test_pack_rejects_an_incomplete_state_dict():
     from clipself_b200 import _lib as L
     lib = L.lib()
