@@ -10,7 +10,9 @@
 //   rounding points of the tcgen05 kernels (oracle/device_arith_oracle.py: softmax_pv);
 //   output: lane l owns dims 2l, 2l+1 (a value row is read as one coalesced 128-byte line), p_j broadcast by shuffle.
 // Also emits the per-(row, head, 16-dim quarter) sum / sum of squares the folded inner_attn_ln needs, like the other
-// attention kernels.
+// attention kernels.  150-160 us at 512 crops x 197 tokens x 12 heads (tools/attn_cls_one.py; 0.6 ms of a cfg2 step); a variant
+// with 16-byte value loads of four keys per instruction (8x the bytes in flight in the P V phase) measured the same, so the
+// per-lane key-row reads of the score phase are what is left to restructure.
 #include "common.cuh"
 
 namespace cs {
