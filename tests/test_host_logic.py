@@ -319,3 +319,20 @@ def test_staged_attention_backward_dataflow_reproduces_autograd():
     for case in [(2, 17, 2, True), (2, 64, 1, False), (1, 130, 1, False)]:
         res = emul.check(*case)
         assert all(v < 2e-2 for v in res.values()), (case, res)
+
+
+def test_bench_flop_model_counts_the_cls_only_last_block():
+    """bench.py reports the reference's algorithmic FLOPs (the contract's metric) and, separately, what the kernels execute:
+    the teacher's last block runs on the CLS row only, which removes ~5.7 % of a cfg2 step's work."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from clipself_b200.tower import TowerCfg
+    cfg = TowerCfg(image_size=224, patch=16, width=768, heads=12, layers=12, hidden=2048, embed_dim=512, pt_seq_len=16, ln_eps=1e-6)
+    algo = bench.flops_per_image(cfg, 32)
+    done = bench.flops_per_image(cfg, 32, executed=True)
+    assert abs(algo / 1e9 - 1228.1) < 0.1                      # SURVEY.md section 8d
+    assert 0.05 < 1.0 - done / algo < 0.065
+    assert bench.flops_per_image(cfg, 0, executed=True) == bench.flops_per_image(cfg, 0)      # the student is not affected
