@@ -156,14 +156,16 @@ class CLIPSelf:
 
         def run_teacher():
             with torch.no_grad():
-                # the features land in a buffer this plug-in owns (consumed by the loss and its backward within the step)
+                # the tower writes into a buffer this plug-in owns (a stable address keeps the native tower's per-buffer CUDA
+                # graphs hot); the loss gets a private copy (4 MB), so a second call before backward() cannot change what
+                # autograd saved
                 edim = dist_model.visual.cfg.embed_dim
                 if self._teacher_out is None or self._teacher_out.shape[0] < R or self._teacher_out.device != device:
                     self._teacher_out = torch.empty(max(R, 1), edim, device=device, dtype=torch.float32)
                 feats = dist_model.visual.forward_chunked(crops, crop_events, out=self._teacher_out[:R])
                 if crop_events is not None:
                     self._crops_free.record()
-                return feats
+                return feats.clone()
 
         # Order: normally the student forward goes first (it only needs the small images, so it overlaps the crop H2D
         # stream).  With the overlapped gradient exchange the frozen teacher goes first: it does not depend on the weights
