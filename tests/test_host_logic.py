@@ -336,3 +336,25 @@ def test_bench_flop_model_counts_the_cls_only_last_block():
     assert abs(algo / 1e9 - 1228.1) < 0.1
     assert 0.05 < 1.0 - done / algo < 0.065
     assert bench.flops_per_image(cfg, 0, executed=True) == bench.flops_per_image(cfg, 0)      # the student is not affected
+
+
+def test_batch_cropper_buffers_keep_their_address():
+    """The on-device cropper hands out views of persistent buffers: same shape -> same storage (the native tower's CUDA graphs
+    and TMA descriptors are cached per address), a larger request re-allocates, a smaller one reuses."""
+    import torch
+    from clipself_b200.crops import _BatchCropper
+    c = _BatchCropper()
+    dev = torch.device("cpu")
+    a = c._buffer(("crops", "out"), (4, 3, 8, 8), torch.float32, dev)
+    b = c._buffer(("crops", "out"), (4, 3, 8, 8), torch.float32, dev)
+    assert a.data_ptr() == b.data_ptr() and a.shape == (4, 3, 8, 8)
+    small = c._buffer(("crops", "out"), (2, 3, 8, 8), torch.float32, dev)
+    assert small.data_ptr() == a.data_ptr() and small.shape == (2, 3, 8, 8)
+    big = c._buffer(("crops", "out"), (8, 3, 8, 8), torch.float32, dev)
+    assert big.numel() == 8 * 3 * 64
+    other = c._buffer(("det", "out"), (4, 3, 8, 8), torch.float32, dev)
+    assert other.data_ptr() != big.data_ptr()
+    x = torch.arange(6, dtype=torch.float32).view(2, 3)
+    assert c.cast(x, torch.float32) is x
+    y = c.cast(x, torch.bfloat16)
+    assert y.dtype == torch.bfloat16 and torch.equal(y.float(), x) and c.cast(x, torch.bfloat16).data_ptr() == y.data_ptr()
