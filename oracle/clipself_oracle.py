@@ -192,6 +192,37 @@ def tower_forward_cls(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg,
     return F.linear(x, sd["head.weight"], sd["head.bias"])
 
 
+def block_cls_only(x: Tensor, sd: Dict[str, Tensor], i: int, cfg: TowerCfg, cos: Tensor, sin: Tensor) -> Tensor:
+    """The CLS row of block(x, ...) computed WITHOUT the other rows' outputs: k and v of every token, one query row through
+    attention, inner LN, proj, norm2 and the SwiGLU MLP (what csrc/tower.cu: block_cls_tail runs for the teacher's last block,
+    since E:565-569 returns norm(x)[:, 0] only).  Returns [B, 1, D]; must equal block(...)[:, :1] (tests/test_oracle_vs_golden)."""
+    p = f"blocks.{i}."
+    B, N, D = x.shape
+    H, hd = cfg.heads, cfg.head_dim
+    u = _ln(x, sd, p + "norm1", cfg.ln_eps)
+    a = p + "attn."
+    q = F.linear(u[:, :1], sd[a + "q_proj.weight"], sd[a + "q_bias"]).reshape(B, 1, H, hd).permute(0, 2, 1, 3)   # CLS: no rotation (E:194-204)
+    k = F.linear(u, sd[a + "k_proj.weight"], None).reshape(B, N, H, hd).permute(0, 2, 1, 3)
+    v = F.linear(u, sd[a + "v_proj.weight"], sd[a + "v_bias"]).reshape(B, N, H, hd).permute(0, 2, 1, 3)
+    k = torch.cat([k[:, :, :1], rope_apply(k[:, :, 1:], cos, sin)], dim=2)
+    att = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(B, 1, D)
+    o = _ln(o, sd, a + "inner_attn_ln", cfg.ln_eps)
+    xc = x[:, :1] + F.linear(o, sd[a + "proj.weight"], sd[a + "proj.bias"])
+    return xc + swiglu(_ln(xc, sd, p + "norm2", cfg.ln_eps), sd, p + "mlp.", cfg.ln_eps)
+
+
+def tower_forward_cls_tail(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg) -> Tensor:
+    """tower_forward_cls with the last block restricted to the CLS row (the form the device runs)."""
+    cos, sin = rope_tables(image_grid(images, cfg), cfg.head_dim, cfg.pt_seq_len)
+    x = embed_tokens(sd, images, cfg)
+    for i in range(cfg.layers - 1):
+        x = block(x, sd, i, cfg, cos, sin)
+    x = block_cls_only(x, sd, cfg.layers - 1, cfg, cos, sin)
+    x = _ln(x, sd, "norm", cfg.ln_eps)[:, 0]
+    return F.linear(x, sd["head.weight"], sd["head.bias"])
+
+
 def tower_encode_dense(sd: Dict[str, Tensor], images: Tensor, cfg: TowerCfg,
                        taps: Dict[str, Tensor] | None = None) -> Tensor:
     """Student dense map, NHWC [B,h,w,C], unit-norm per token (E:588-623)."""

@@ -174,3 +174,24 @@ def test_device_arith_oracle_step_gradients_flow():
     assert abs(out["loss"].item() - ref["loss"].item()) < 5e-3 * abs(ref["loss"].item())
     assert ssd["blocks.0.mlp.w3.weight"].grad.abs().sum() > 0
     assert ssd[f"blocks.{cfg.layers - 1}.attn.q_proj.weight"].grad is None      # grad-less in the reference too
+
+
+@pytest.mark.parametrize("tag", ["tiny_grid", "cfg1_b16"])
+def test_cls_only_last_block_is_the_reference_teacher(golden, tag):
+    """The device runs the teacher's last block on the CLS row only (eva_vit_model.py:565-569 reads nothing else).  The
+    restatement of that form must reproduce the reference's teacher features of the fixture and the full-form oracle."""
+    from oracle import clipself_oracle as O
+    cases = {"tiny_grid": (O.CFG_TINY, 2, 4, "grid"), "cfg1_b16": (O.CFG_B16, 2, 8, "grid")}
+    ocfg, B, K, kind = cases[tag]
+    g = golden(tag)
+    seed = int(g["seed"])
+    _, boxes, crops = O.synth_batch(ocfg, B, K, seed + 2, kind=kind, ragged=False)
+    _, idx = O.extract_rois(boxes)
+    tc = crops.flatten(0, 1)[idx]
+    sd = O.synth_tower_weights(ocfg, seed + 1)
+    with torch.no_grad():
+        tail = O.tower_forward_cls_tail(sd, tc, ocfg)
+        full = O.tower_forward_cls(sd, tc, ocfg)
+    torch.testing.assert_close(tail, full, rtol=1e-4, atol=1e-5)
+    ref = torch.from_numpy(np.asarray(g["teacher"]))
+    assert ((tail - ref).norm() / ref.norm()).item() < 2e-3
