@@ -27,5 +27,5 @@ for _ in range(5):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 t = sorted(ts)[2]
-print(f"attention bwd B={B} N={N} H={H} tc={os.environ.get('CS_ATTN_BWD_TC', '0')}: {t*1e3:.1f} us, "
+print(f"attention bwd B={B} N={N} H={H} legacy={os.environ.get('CS_ATTN_LEGACY', '0')}: {t*1e3:.1f} us, "
       f"{10.0*B*H*N*N*64/t/1e9:.1f} TFLOP/s (useful, 5 contractions)")
